@@ -1,0 +1,89 @@
+"""CPU: the Tier-1 oracle (oracle/torch_oracle.py) against fixtures minted from the real
+reference (oracle/make_goldens.py).  Flags, ids and height-field indices are compared bit-exact;
+floats at fp32 rounding level (the oracle repeats the reference's op sequence on the same
+device, so most are bit-equal too)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_case_inputs, load_golden
+from oracle import torch_oracle as O
+from oracle.make_goldens import ENV_CASES
+
+EXACT = ("reset_buf", "time_out_buf", "contact_filt", "last_contacts", "episode_length_buf")
+FLOATS = ("base_lin_vel", "base_ang_vel", "projected_gravity", "measured_heights", "rew_buf",
+          "feet_air_time", "commands", "obs_buf", "privileged_obs_buf", "last_actions",
+          "last_last_actions", "last_dof_pos", "last_dof_vel", "last_torques", "last_root_vel",
+          "episode_sums")
+
+
+@pytest.mark.parametrize("case", ENV_CASES, ids=[c["name"] for c in ENV_CASES])
+def test_env_case(case):
+    gold = load_golden(f"env_{case['name']}.npz")
+    cfg, hf, state, noise, targets, delayed, chk = build_case_inputs(case)
+    assert chk == gold["input_checksum"], "synthetic generator drifted from the minted inputs"
+    env = O.OracleEnv(cfg, state, hf)
+    tq = torch.stack([env._compute_torques(delayed[:, k]) for k in range(4)], dim=1)
+    np.testing.assert_allclose(tq.numpy(), gold["torques4"], rtol=1e-6, atol=1e-6)
+    if not cfg.is_plane:
+        env._get_heights()
+        px, py = env.last_height_indices
+        np.testing.assert_array_equal(px.numpy(), gold["px"].astype(np.int64))
+        np.testing.assert_array_equal(py.numpy(), gold["py"].astype(np.int64))
+    ids, term_obs, term_amp = env.post_physics_step(noise, None if case.get("no_reset") else targets)
+    np.testing.assert_array_equal(ids.numpy(), gold["env_ids"])
+    np.testing.assert_allclose(term_obs.numpy(), gold["term_obs"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(term_amp.numpy(), gold["term_amp"], rtol=1e-6, atol=1e-6)
+    snap = env.snapshot()
+    for k in EXACT:
+        np.testing.assert_array_equal(snap[k].numpy(), gold[k], err_msg=k)
+    for k in FLOATS:
+        np.testing.assert_allclose(snap[k].numpy(), gold[k], rtol=1e-6, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c", "alldone"])
+def test_gae(name):
+    from isaacgymloco_b200 import synthetic as S
+    gold = load_golden("gae.npz")
+    n, t, seed, gamma, lam = gold[f"{name}_meta"]
+    r = S.make_rollout(int(n), int(t), int(seed))
+    if name == "alldone":
+        r["dones"][:] = 1
+    ret, adv = O.compute_returns(r["rewards"], r["values"], r["dones"], r["last_values"], gamma, lam)
+    np.testing.assert_array_equal(ret.numpy(), gold[f"{name}_returns"])
+    np.testing.assert_array_equal(adv.numpy(), gold[f"{name}_advantages"])
+
+
+def _table(gold):
+    clips = [torch.from_numpy(gold[f"clip{i}"]) for i in range(len(gold["frame_durations"]))]
+    return O.OracleMotionTable(clips, gold["frame_durations"], gold["weights_raw"], 0.02)
+
+
+def test_amp_blend():
+    gold = load_golden("amp.npz")
+    tab = _table(gold)
+    np.testing.assert_array_equal(tab.trajectory_lens, gold["lens"])
+    np.testing.assert_array_equal(tab.trajectory_weights, gold["weights"])
+    frames, lo, hi = tab.get_full_frame_at_time_batch(gold["blend_idx"], gold["blend_times"])
+    np.testing.assert_array_equal(frames.numpy(), gold["blend_frames"])
+
+
+def test_amp_pairs_and_reward():
+    gold = load_golden("amp.npz")
+    pre_s, pre_sn = torch.from_numpy(gold["pre_s"]), torch.from_numpy(gold["pre_s_next"])
+    for k in (0, 1):
+        s, sn = O.amp_pairs(pre_s, pre_sn, gold[f"pair_idx{k}"])
+        np.testing.assert_array_equal(s.numpy(), gold[f"pair_s{k}"])
+        np.testing.assert_array_equal(sn.numpy(), gold[f"pair_sn{k}"])
+    # normaliser moments (utils.py:90-110)
+    mean, var, count = np.zeros(30), np.ones(30), 1e-4
+    for k in (0, 1):
+        mean, var, count = O.running_moments_update(mean, var, count, gold[f"pair_s{k}"])
+    np.testing.assert_array_equal(mean, gold["norm_mean"])
+    np.testing.assert_array_equal(var, gold["norm_var"])
+    x = O.amp_disc_input(torch.from_numpy(gold["disc_s"]), torch.from_numpy(gold["disc_sn"]),
+                         gold["norm_mean"], gold["norm_var"])
+    np.testing.assert_array_equal(x.numpy(), gold["disc_x"])
+    r = O.amp_reward_from_logit(torch.from_numpy(gold["disc_d"]), torch.from_numpy(gold["disc_task_r"]),
+                                0.01, 0.3)
+    np.testing.assert_array_equal(r.numpy(), gold["disc_r"])
