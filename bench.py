@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- post-physics + GAE env-steps/s (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+    python bench.py --impl reference --steps K --warmup W    (the reference arm: CPU torch)
+
+One *step* = one rollout iteration of the hot path for this rank's env shard:
+    T x { 4 x PD torques (decimation) ; fused post-physics ; reset-id compaction ; terminal rows ;
+          post-reset fix-up }  +  HIMRolloutStorage.compute_returns (GAE scan + normalisation)
+on synthetic, seeded PhysX state.  One *env-step* = one env through one of the T
+inner steps (+ 1/T of the GAE).  Rank r owns a contiguous shard of the global env set (weak
+scaling: --envs per GPU); for N>1 the advantage moments are all-reduced every step and the 20
+flat PPO-gradient all-reduces of one update (545,660 fp32) run on a side stream.
+
+JSON line (rank 0): see the driver contract; extra keys `roofline` (dominant kernel, CUDA-event
+timed inside the timed region) and `cpu_baseline` (the torch oracle port on the host cores).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "post_physics_gae_env_steps_per_s"
+UNIT = "env-steps/s"
+AC_PARAMS = 545_660          # HIMActorCritic incl. estimator
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_rollout_runner(n_envs, t_len, seed=1234):
+    """The reference's torch implementation of the path, restated (oracle/torch_oracle.py; the
+    Python reference itself cannot travel to the GPU box), on all host cores.  Returns a callable
+    running ONE rollout (T x {4 torques, post_physics_step} + compute_returns)."""
+    from isaacgymloco_b200 import config as C, synthetic as S
+    from oracle import torch_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = C.aliengo("flat", num_envs=n_envs, index_math=C.INDEX_MATH_TORCH_CPU)
+    hf = S.make_terrain(cfg, seed=1)
+    state = S.make_state(cfg, n_envs, hf, seed=seed)
+    env = O.OracleEnv(cfg, state, hf)
+    roll = S.make_rollout(n_envs, t_len, seed)
+    delayed = env.actions.view(n_envs, 1, 12).repeat(1, 4, 1)
+
+    def one_rollout():
+        for _ in range(t_len):
+            for k in range(4):
+                env.torques = env._compute_torques(delayed[:, k])
+            noise = dict(term45=torch.rand(n_envs, 45), term187=torch.rand(n_envs, 187),
+                         obs45=torch.rand(n_envs, 45), obs187=torch.rand(n_envs, 187))
+            env.post_physics_step(noise, None)
+        O.compute_returns(roll["rewards"], roll["values"], roll["dones"], roll["last_values"], 0.99, 0.95)
+
+    return one_rollout, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_envs, t_len = 4096, args.rollout
+    fn, cores = cpu_rollout_runner(n_envs, t_len)
+    for _ in range(args.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    value = n_envs * t_len * args.steps / dt
+    sample = f"{n_envs} of {args.envs} envs x {t_len}-step rollout per step (oracle/torch_oracle.py, torch CPU)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world=args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"aliengo flat, {args.envs} envs/GPU x {args.rollout}-step synthetic rollout: 4x PD torque + fused "
+                        f"post-physics (45-dim obs, 6-step history, 187-pt scan, 21 reward terms) per env-step, GAE per rollout",
+            "baseline_config": "configs[4] at N GPUs (65,536 envs/GPU; the roofline-target size, inputs 323 MB/step > 126 MB L2); "
+                               "configs[1] (4096 envs) is L2-resident and reported under `latency_4096`",
+            "envs_per_gpu": args.envs, "global_envs": args.envs * world, "rollout_len": args.rollout,
+            "l2_policy": "inputs larger than L2 (no flush needed)" if args.envs >= 32768 else "L2-resident (latency regime)",
+            "noise": "in-kernel Philox", "parallelism": f"env-shard x{world}"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+class Workload:
+    def __init__(self, envs, t_len, rank, world, device, seed=1234):
+        from isaacgymloco_b200 import config as C, synthetic as S
+        from isaacgymloco_b200.legged_robot import FusedLeggedRobot
+        from isaacgymloco_b200.rollout_storage import HIMRolloutStorage
+        self.envs, self.t_len, self.world, self.device = envs, t_len, world, device
+        self.cfg = C.aliengo("flat", num_envs=envs * world, env_id_offset=rank * envs)
+        hf = S.make_terrain(self.cfg, seed=1)
+        state = S.make_state(self.cfg, envs, hf, seed=seed + rank, env_id_offset=rank * envs)
+        self.host_state = state
+        self.env = FusedLeggedRobot(self.cfg, state, hf, device=device, seed=seed)
+        self.env.disturbance[:, 0, :] = 0.0
+        self.storage = HIMRolloutStorage(envs, t_len, [270], [self.env.num_privileged_obs], [12], device=device,
+                                         shard_statistics=world > 1)
+        roll = S.make_rollout(envs, t_len, seed + rank)
+        self.storage.rewards.copy_(roll["rewards"]); self.storage.values.copy_(roll["values"])
+        self.storage.dones.copy_(roll["dones"])
+        self.last_values = roll["last_values"].to(device)
+        self.env._delay_actions()
+        self.fused_ms = []            # CUDA-event pairs around the dominant kernel
+        self.launches = 0
+
+    def env_step(self, time_fused=False):
+        import ctypes
+        from isaacgymloco_b200 import _lib as L
+        env = self.env
+        for k in range(env.cfg.decimation):
+            env._compute_torques_into(env.delayed_actions[:, k], env.torques)
+        c, b = ctypes.byref(env._c), ctypes.byref(env._buffers())
+        if time_fused:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        L.check(L.lib.hl_post_physics_fused(c, b, env.num_envs, L.stream()))
+        if time_fused:
+            e1.record()
+            self.fused_ms.append((e0, e1))
+        L.check(L.lib.hl_select_reset_ids(L.ptr(env.reset_buf), env.num_envs, L.ptr(env._reset_ids), L.ptr(env._n_reset),
+                                          L.ptr(env._select_ws), L.stream()))
+        env._terminal_rows(env._reset_ids, env._n_reset)
+        env.fused_post_reset()
+        env.common_step_counter += 1
+        self.launches += env.cfg.decimation + 4
+
+    def rollout(self, time_fused=False):
+        for _ in range(self.t_len):
+            self.env_step(time_fused)
+        self.storage.compute_returns(self.last_values, self.cfg.gamma, self.cfg.lam)
+        self.launches += 2
+
+
+def timed(fn, iters, sync_dist):
+    """K calls of fn bracketed by barrier + synchronize, timed with CUDA events on the launch stream."""
+    import torch.distributed as dist
+    if sync_dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if sync_dist:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if sync_dist:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from isaacgymloco_b200 import dist as D
+    from isaacgymloco_b200 import roofline as R
+    rank, world, local = D.init_from_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    wl = Workload(args.envs, args.rollout, rank, world, device)
+    bytes_tab = R.per_env_step_bytes(wl.cfg, args.rollout)
+
+    # multi-GPU exchange: 20 flat-gradient all-reduces per update on a side stream (synthetic grads)
+    comm_stream = torch.cuda.Stream() if world > 1 else None
+    grads = torch.randn(AC_PARAMS, device=device) if world > 1 else None
+
+    def step():
+        if world > 1:
+            comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm_stream):
+                for _ in range(20):
+                    dist.all_reduce(grads, op=dist.ReduceOp.AVG)
+        wl.rollout(time_fused=True)
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(comm_stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    wl.fused_ms.clear()
+    wl.launches = 0
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = timed(step, args.steps, world > 1)
+    clocks = sampler.stop() if sampler else None
+    launches = wl.launches
+    fused = [a.elapsed_time(b) for a, b in wl.fused_ms]
+    value = world * args.envs * args.rollout * args.steps / (ms * 1e-3)
+
+    # ---- CUDA-graph replay of the same rollout (launch-overhead-free; informational)
+    graph_info = None
+    if world == 1 and not args.no_graph:
+        try:
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                wl.rollout()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g, stream=s):
+                    wl.rollout()
+            torch.cuda.current_stream().wait_stream(s)
+            for _ in range(3):
+                g.replay()
+            gms = timed(g.replay, args.steps, False)
+            graph_info = {"value": args.envs * args.rollout * args.steps / (gms * 1e-3), "unit": UNIT,
+                          "ms_per_step": gms / args.steps}
+        except Exception as ex:  # pragma: no cover
+            graph_info = {"error": str(ex)[:200]}
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    fused_avg_ms = sum(fused) / max(len(fused), 1)
+    alg_bytes = bytes_tab["post_physics"] * args.envs
+    achieved = alg_bytes / (fused_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "hl_post_physics_fused_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": args.traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": fused_avg_ms,
+                "bytes_per_env_step": bytes_tab,
+                "whole_step_frac": (bytes_tab["total"] * args.envs * args.rollout * args.steps / (ms * 1e-3) / 1e9) / peak}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
+        "gpu_launches": launches, "roofline": roofline,
+    }
+    if graph_info:
+        line["cuda_graph"] = graph_info
+
+    # ---- e2e: the public API with HOST buffers (pinned), H2D of the PhysX tensors + actions and
+    # D2H of obs / privileged obs / rewards / dones every env-step, inside the timed region
+    if not args.no_e2e:
+        line["e2e"] = measure_e2e(wl, args, world)
+    # ---- 4096-env latency regime (configs[1]) and the CPU baseline: rank 0, N=1 only
+    if world == 1:
+        if not args.no_latency:
+            line["latency_4096"] = measure_latency_4096(args)
+        if not args.no_cpu:
+            fn, cores = cpu_rollout_runner(4096, args.rollout)
+            fn()
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                fn()
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 4096 * args.rollout * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{reps} rollouts of 4096 envs x {args.rollout} steps (configs[0]) after 1 warm-up, "
+                                              f"oracle/torch_oracle.py on torch CPU"}
+    print(json.dumps(line), flush=True)
+
+
+def measure_e2e(wl, args, world):
+    import torch.distributed as dist
+    env = wl.env
+    names_in = ("root_states", "dof_state", "contact_forces", "rigid_body_states", "actions")
+    host_in = {k: wl.host_state[k].contiguous().pin_memory() for k in names_in}
+    dev_in = {k: getattr(env, k) for k in names_in}
+    outs = {"obs_buf": env.obs_buf, "privileged_obs_buf": env.privileged_obs_buf, "rew_buf": env.rew_buf, "reset_buf": env.reset_buf}
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outs.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+
+    def e2e_step():
+        for k in names_in:
+            dev_in[k].view(-1).copy_(host_in[k].view(-1), non_blocking=True)
+        env._delay_actions()
+        for k in range(env.cfg.decimation):
+            env._compute_torques_into(env.delayed_actions[:, k], env.torques)
+        env.post_physics_step()                      # public API (includes the reference's host sync on the reset count)
+        for k, v in outs.items():
+            host_out[k].copy_(v, non_blocking=True)
+
+    def e2e_rollout():
+        for _ in range(wl.t_len):
+            e2e_step()
+        wl.storage.compute_returns(wl.last_values, wl.cfg.gamma, wl.cfg.lam)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_rollout()
+    iters = max(1, min(args.steps, 3))
+    ms = timed(e2e_rollout, iters, world > 1)
+    return {"value": world * args.envs * wl.t_len * iters / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * wl.t_len,
+            "d2h_bytes_per_step": d2h * wl.t_len, "rollouts": iters, "ms_per_step": ms / iters,
+            "api": "FusedLeggedRobot._compute_torques x4 + post_physics_step per env-step, HIMRolloutStorage.compute_returns per rollout"}
+
+
+def measure_latency_4096(args):
+    """configs[1]: 4096 envs on one B200 -- the working set (20 MB) is L2-resident, so this is a
+    latency number (CUDA-graph replay of one rollout), not a roofline one."""
+    wl = Workload(4096, args.rollout, 0, 1, torch.device("cuda", torch.cuda.current_device()))
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        wl.rollout()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            wl.rollout()
+    torch.cuda.current_stream().wait_stream(s)
+    for _ in range(5):
+        g.replay()
+    iters = 20
+    ms = timed(g.replay, iters, False)
+    direct = timed(wl.rollout, 5, False)
+    return {"envs": 4096, "rollout_len": args.rollout, "us_per_env_step_graph": 1e3 * ms / iters / args.rollout,
+            "value_graph": 4096 * args.rollout * iters / (ms * 1e-3), "value_direct_launch": 4096 * args.rollout * 5 / (direct * 1e-3),
+            "unit": UNIT}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
+    ap.add_argument("--rollout", type=int, default=24, help="T: env-steps per rollout")
+    ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per fused launch (from profiles/)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    if args.traffic is None:
+        p = os.path.join(ROOT, "profiles", "fused_traffic.json")
+        if os.path.exists(p):
+            args.traffic = json.load(open(p)).get("dram_bytes_per_launch")
+    run_gpu_arm(args)
+    if torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,266 @@
+/* himloco_b200.h -- C ABI of libhimloco_b200.so (hand-written sm_100a CUDA kernels for the
+ * post-physics + GAE + AMP hot path of the HIMLoco legged_gym / rsl_rl stack).
+ *
+ * The reference (xyyandhtl/IsaacgymLoco) has no FFI layer for this path: the boundary is Python
+ * bound methods mutating `self.*` tensors.  Each entry point below names the
+ * reference method it replaces; paths are relative to the reference root, LR =
+ * legged_gym/legged_gym/envs/base/legged_robot.py.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - the library never allocates or frees caller-visible memory and never synchronises;
+ *  - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*);
+ *    every call is CUDA-graph capturable;
+ *  - return value 0 = success, otherwise an HL_E_* code; hl_last_error() gives the message
+ *    (thread-local).  No exceptions cross the ABI.
+ *  - tensors are consumed in Isaac Gym's own AoS layouts (LR:929-944).
+ */
+#ifndef HIMLOCO_B200_H_
+#define HIMLOCO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HL_VERSION 100
+
+#define HL_OK 0
+#define HL_E_INVALID 1   /* bad argument / inconsistent config */
+#define HL_E_CUDA 2      /* a CUDA runtime call or launch failed */
+#define HL_E_UNSUPPORTED 3
+
+#define HL_MAX_TERMS 64
+#define HL_MAX_PTS 32
+#define HL_MAX_BODIES_IDX 16
+#define HL_NUM_DOF 12
+#define HL_NUM_FEET 4
+#define HL_OBS_STEP 45        /* one-step observation (LR:385-391)            */
+#define HL_OBS_HISTORY 6      /* obs_buf = 6 x 45, newest first (LR:403)       */
+#define HL_PRIV_OBS 238       /* 45 + 3 + 3 + 187 (LR:397-404)                 */
+#define HL_AMP_OBS 30         /* LR:416                                        */
+#define HL_AMP_FRAME 49       /* rsl_rl/rsl_rl/datasets/motion_loader.py:17-48 */
+
+/* index-path arithmetic flavour (see DESIGN.md "bit-exact indices") */
+#define HL_INDEX_MATH_TORCH_CUDA 0
+#define HL_INDEX_MATH_TORCH_CPU 1
+
+/* stages of hl_post_physics_stages (bit mask) -- one per reference method */
+#define HL_ST_COUNTERS 0x001u    /* episode_length_buf += 1                     LR:193        */
+#define HL_ST_FRAME 0x002u       /* base_lin_vel/base_ang_vel/projected_gravity LR:197-200    */
+#define HL_ST_CONTACTS 0x004u    /* contact, contact_filt, last_contacts, feet  LR:203-209    */
+#define HL_ST_HEADING 0x008u     /* commands[:,2] from heading error            LR:616-620    */
+#define HL_ST_HEIGHTS 0x010u     /* measured_heights = _get_heights()           LR:1318-1355  */
+#define HL_ST_TERMINATION 0x020u /* check_termination()                         LR:249-286    */
+#define HL_ST_REWARD 0x040u      /* compute_reward() + all _reward_* terms      LR:363-380    */
+#define HL_ST_OBS 0x080u         /* compute_observations()                      LR:382-404    */
+#define HL_ST_OBS_NOSHIFT 0x100u /* with HL_ST_OBS: overwrite slot 0 only, keep the history   */
+#define HL_ST_OBS_CLIP 0x200u    /* clip +-clip_observations (end of step())    LR:167-171    */
+#define HL_ST_ROLL 0x400u        /* disturbance=0, last_* <- current            LR:235-241    */
+#define HL_ST_BASE_HEIGHT 0x800u /* base_height_out = _get_base_heights()       LR:1357-1398  */
+#define HL_ST_ALL_STEP (HL_ST_COUNTERS | HL_ST_FRAME | HL_ST_CONTACTS | HL_ST_HEADING | HL_ST_HEIGHTS | \
+                        HL_ST_TERMINATION | HL_ST_REWARD | HL_ST_OBS | HL_ST_OBS_CLIP | HL_ST_ROLL)
+
+/* Plain-old-data config; built once from the reference's cfg object (scales already x dt,
+ * LR:1041-1046).  Field order is mirrored by isaacgymloco_b200/config.py::HlCfg. */
+typedef struct HlCfg {
+  int32_t struct_bytes;          /* = sizeof(HlCfg): ABI guard */
+  int32_t num_bodies;            /* 17 for aliengo */
+  int32_t control_type;          /* 0 = "P", 1 = "V", 2 = "T"   (LR:676-687) */
+  int32_t only_positive_rewards; /* LR:374 */
+  int32_t n_terms;               /* active reward terms, excluding `termination` */
+  int32_t has_termination_term;  /* LR:377 */
+  int32_t add_noise;             /* LR:393 */
+  int32_t mesh_type;             /* 0 plane, 1 heightfield/trimesh (LR:1331) */
+  int32_t measure_heights;
+  int32_t terrain_rows, terrain_cols; /* height_samples.shape */
+  int32_t term_base_vel_violate, term_out_of_border, term_fall_down; /* LR:266,275,282 */
+  int32_t heading_command;       /* LR:616 */
+  int32_t index_math;            /* HL_INDEX_MATH_* */
+  int32_t n_px, n_py;            /* measured_points_x / _y counts (17, 11) */
+  int32_t n_bx, n_by;            /* base height grid (7, 9; LR:1308-1309) */
+  int32_t n_penalised, n_term_contact;
+  int32_t feet_idx[HL_NUM_FEET];
+  int32_t penalised_idx[HL_MAX_BODIES_IDX];
+  int32_t term_contact_idx[HL_MAX_BODIES_IDX];
+  int32_t term_id[HL_MAX_TERMS]; /* HlTerm ids in accumulation (alphabetical) order */
+  int64_t max_episode_length;
+  int64_t env_id_offset;         /* global id of local env 0 (env-sharded multi-GPU) */
+  int64_t stairsup_start, stairsup_end, pit_start, gap_end; /* global slices, LR:71-90 */
+  float dt, action_scale, hip_reduction, sim_dt;
+  float soft_dof_vel_limit, soft_torque_limit, tracking_sigma, base_height_target;
+  float foot_height_target_base, foot_height_target_terrain, max_contact_force;
+  float termination_scale;
+  float obs_lin_vel, obs_ang_vel, obs_dof_pos, obs_dof_vel, obs_height, clip_obs;
+  float noise_height;            /* noise_scale_vec[45:232] (uniform) */
+  float horizontal_scale, inv_horizontal_scale, vertical_scale, border_size;
+  float x_limit, y_limit;        /* terrain.py:226 */
+  float commands_scale[3];
+  float p_gains[HL_NUM_DOF], d_gains[HL_NUM_DOF], torque_limits[HL_NUM_DOF];
+  float default_dof_pos[HL_NUM_DOF], dof_pos_lo[HL_NUM_DOF], dof_pos_hi[HL_NUM_DOF];
+  float dof_vel_limits[HL_NUM_DOF];
+  float noise45[HL_OBS_STEP];    /* noise_scale_vec[0:45], LR:901-906 */
+  float term_scale[HL_MAX_TERMS];
+  float px[HL_MAX_PTS], py[HL_MAX_PTS], bx[HL_MAX_PTS], by[HL_MAX_PTS];
+} HlCfg;
+
+/* Device buffers of one env shard, named after the LeggedRobot attributes they are. */
+typedef struct HlEnvBuffers {
+  int32_t struct_bytes;
+  int32_t _pad;
+  /* PhysX state (read-only), LR:929-944 */
+  const float* root_states;       /* (N,13)  pos3 quat_xyzw4 lin3 ang3 */
+  const float* dof_state;         /* (N,12,2) interleaved pos,vel      */
+  const float* contact_forces;    /* (N,B,3)                            */
+  const float* rigid_body_states; /* (N,B,13)                           */
+  /* terrain */
+  const int16_t* height_samples;  /* (rows,cols) int16, x -> rows       */
+  const int16_t* height_min3;     /* (rows-1,cols-1) from hl_terrain_prepare; may be NULL */
+  /* policy-side state */
+  const float* actions;           /* (N,12) */
+  float* last_actions;            /* (N,12) */
+  float* last_last_actions;       /* (N,12) */
+  float* last_dof_pos;            /* (N,12) */
+  float* last_dof_vel;            /* (N,12) */
+  const float* torques;           /* (N,12) */
+  float* last_torques;            /* (N,12) */
+  float* last_root_vel;           /* (N,6)  */
+  float* commands;                /* (N,4)  */
+  int64_t* episode_length_buf;    /* (N,)   */
+  uint8_t* last_contacts;         /* (N,4) bool */
+  uint8_t* contact_filt;          /* (N,4) bool */
+  float* feet_air_time;           /* (N,4)  */
+  float* disturbance;             /* (N,B,3); only [:,0,:] is read/zeroed */
+  const int64_t* terrain_levels;  /* (N,)   */
+  float* episode_sums;            /* (R,N): rows follow cfg term order, `termination` last */
+  /* derived state */
+  float* base_lin_vel;            /* (N,3) */
+  float* base_ang_vel;            /* (N,3) */
+  float* projected_gravity;       /* (N,3) */
+  float* measured_heights;        /* (N,n_px*n_py) */
+  float* feet_pos;                /* (N,4,3) optional (NULL = not materialised) */
+  float* feet_vel;                /* (N,4,3) optional */
+  uint8_t* reset_buf;             /* (N,) bool */
+  uint8_t* time_out_buf;          /* (N,) bool */
+  float* rew_buf;                 /* (N,)  */
+  const float* obs_buf_in;        /* (N,270) previous history            */
+  float* obs_buf_out;             /* (N,270) may alias obs_buf_in        */
+  float* privileged_obs_buf;      /* (N,238) */
+  /* observation noise: pre-drawn U[0,1) tensors (parity mode) or NULL => in-kernel Philox */
+  const float* noise_u45;         /* (N,45)  */
+  const float* noise_u187;        /* (N,187) */
+  uint64_t philox_seed;
+  uint64_t philox_offset;         /* advance by 1 per step */
+  int32_t* height_idx_out;        /* optional debug: (N,n_px*n_py,2) clipped (px,py) */
+  float* base_height_out;         /* (N,) written by HL_ST_BASE_HEIGHT */
+} HlEnvBuffers;
+
+int hl_version(void);
+const char* hl_last_error(void);
+/* sizeof() of the structs as compiled into the library (binding self-check) */
+int hl_sizeof_cfg(void);
+int hl_sizeof_env_buffers(void);
+
+/* LeggedRobot._compute_torques(actions) -- LR:658-688.
+ * `actions` is row-strided (a column slice of delayed_actions (N,4,12), LR:146). */
+int hl_pd_torque(const HlCfg* cfg, const float* actions, int64_t actions_row_stride,
+                 const float* dof_state, const float* motor_strength, const float* kp_factors,
+                 const float* kd_factors, const float* last_dof_vel, float* torques_out,
+                 float* joint_pos_target_out /* may be NULL */, int64_t n_envs, void* stream);
+
+/* One-off per terrain: min3[px,py] = min(h[px,py], h[px+1,py], h[px,py+1]) (LR:1349-1353),
+ * shape (rows-1, cols-1); turns the three gathers of every height sample into one. */
+int hl_terrain_prepare(const int16_t* height_samples, int32_t rows, int32_t cols,
+                       int16_t* height_min3_out, void* stream);
+
+/* The fused post-physics step: every HL_ST_* stage for all envs in ONE kernel
+ * (LeggedRobot.post_physics_step LR:178-247 minus the RNG/PhysX-driven calls, plus the obs clip
+ * of step() LR:167-171).  Observations are written speculatively for every env; envs that reset
+ * are patched afterwards by hl_post_reset_fixup. */
+int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n_envs, void* stream);
+
+/* Any subset of stages, for the individual drop-in methods (check_termination(),
+ * compute_reward(), compute_observations(), _get_heights(), ...).  If `env_ids` is non-NULL the
+ * stages run only for ids[0 .. *n_ids_dev). */
+int hl_post_physics_stages(const HlCfg* cfg, const HlEnvBuffers* bufs, uint32_t stages,
+                           const int64_t* env_ids, const int32_t* n_ids_dev, int64_t n_envs,
+                           void* stream);
+
+/* env_ids = reset_buf.nonzero().flatten() -- LR:225.  Ascending int64 ids + count, on device.
+ * workspace: hl_select_workspace_bytes(n) bytes. */
+int64_t hl_select_workspace_bytes(int64_t n_envs);
+int hl_select_reset_ids(const uint8_t* reset_buf, int64_t n_envs, int64_t* ids_out,
+                        int32_t* count_out, void* workspace, void* stream);
+
+/* compute_termination_observations(env_ids) (LR:439-460) and get_amp_observations()[env_ids]
+ * (LR:228,406-416) for the compacted reset set, from the PRE-reset state.
+ * noise: pre-drawn (N,45)/(N,187) U[0,1) indexed by env id, or NULL => Philox stream 1. */
+int hl_terminal_rows(const HlCfg* cfg, const HlEnvBuffers* bufs, const int64_t* env_ids,
+                     const int32_t* n_ids_dev, const float* term_noise_u45,
+                     const float* term_noise_u187, float* term_priv_obs_out /* (cap,238) */,
+                     float* term_amp_out /* (cap,30) or NULL */, int64_t n_envs, void* stream);
+
+/* After reset_idx mutated the reset envs: re-scan their heights (LR:332-333), rewrite slot 0 of
+ * obs_buf and privileged_obs_buf from the post-reset state (stale base velocities, LR:232) and
+ * redo the end-of-step roll for them (LR:235-241). */
+int hl_post_reset_fixup(const HlCfg* cfg, const HlEnvBuffers* bufs, const int64_t* env_ids,
+                        const int32_t* n_ids_dev, int64_t n_envs, void* stream);
+
+/* get_amp_observations() for all envs -- LR:406-416: (N,30) = dof_pos, base_lin_vel,
+ * base_ang_vel, dof_vel. */
+int hl_amp_observations(const float* dof_state, const float* base_lin_vel, const float* base_ang_vel,
+                        float* amp_obs_out, int64_t n_envs, void* stream);
+
+/* HIMRolloutStorage.compute_returns(last_values, gamma, lam) --
+ * rsl_rl/rsl_rl/storage/him_rollout_storage.py:113-127 (== amp_rollout_storage.py:141-155).
+ * Step 1: reverse-time GAE scan; writes returns and raw advantages (T,N,1) and accumulates
+ * moments[0..2] = (sum adv, sum adv^2, count) in float64 (caller zeroes `moments` first; when
+ * env-sharded, all-reduce them before step 2).  Step 2: (adv - mean) / (std_unbiased + 1e-8). */
+int hl_gae_scan(const float* rewards, const float* values, const uint8_t* dones,
+                const float* last_values, float* returns, float* advantages, double* moments,
+                int32_t t_len, int64_t n_envs, float gamma, float lam, void* stream);
+int hl_adv_normalize(float* advantages, const double* moments, int64_t n_elems, void* stream);
+
+/* AMPLoader.get_full_frame_at_time_batch(traj_idxs, times) --
+ * rsl_rl/rsl_rl/datasets/motion_loader.py:231-255 with quaternion_slerp
+ * rsl_rl/rsl_rl/utils/utils.py:153-186.  `frames` = all clips stacked (sum n_i, 49);
+ * clip i starts at row clip_offset[i]; lens/num_frames are the float64 arrays of the loader. */
+int hl_amp_frame_blend(const float* frames, const int32_t* clip_offset, const double* clip_len,
+                       const double* clip_num_frames, int32_t n_clips, const int64_t* traj_idxs,
+                       const double* times, float* out /* (B,49) */,
+                       int32_t* idx_low_out /* optional (B,) */, int32_t* idx_high_out, int64_t batch,
+                       void* stream);
+
+/* AMPLoader.feed_forward_generator preload branch -- motion_loader.py:321-330: for each idx, the
+ * 30 AMP columns [7:19] + [31:49] of preloaded_s and preloaded_s_next. */
+int hl_amp_gather_pairs(const float* preloaded_s, const float* preloaded_s_next, int64_t n_preloaded,
+                        const int64_t* idxs, float* s_out, float* s_next_out, int64_t batch,
+                        void* stream);
+
+/* AMPDiscriminator.predict_amp_reward input assembly -- amp_discriminator.py:59-63 with
+ * Normalizer.normalize_torch utils.py:124-130 and the runner's terminal patch
+ * hybrid_runner.py:191-192 fused in: row i of next_state is taken from terminal_states[j] when
+ * env i == reset_ids[j].  mean/std are (30,) fp32 (std = sqrt(fp32(var + eps))).
+ * Any of mean/std may be NULL (normalizer=None). */
+int hl_amp_disc_input(const float* state, const float* next_state, const float* mean, const float* std_,
+                      float clip, const int64_t* reset_ids, const int32_t* n_reset_dev,
+                      const float* terminal_states, float* next_state_patched_out /* optional */,
+                      float* x_out /* (N,60) */, int64_t n_envs, void* stream);
+
+/* ... and its epilogue -- amp_discriminator.py:64-68,70-72:
+ * r = coef * clamp(1 - (d-1)^2/4, min 0); if lerp > 0: r = (1-lerp) r + lerp task_r. */
+int hl_amp_reward(const float* d_logits, const float* task_reward, float coef, float lerp,
+                  float* reward_out, int64_t n_envs, void* stream);
+
+/* RunningMeanStd.update moments of one batch -- utils.py:90-94: per-column mean and (biased)
+ * variance of x (M,D) in float64; out = [mean(D), var(D)].  Scratch: 2*D*grid doubles provided by
+ * the caller via hl_moments_workspace_bytes. */
+int64_t hl_moments_workspace_bytes(int32_t dim);
+int hl_column_moments(const float* x, int64_t rows, int32_t dim, double* mean_var_out,
+                      void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIMLOCO_B200_H_ */

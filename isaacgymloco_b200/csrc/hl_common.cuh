@@ -1,0 +1,76 @@
+// Shared device helpers for libhimloco_b200 (sm_100a).  See include/himloco_b200.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/himloco_b200.h"
+
+// ----------------------------------------------------------------------------- errors
+void hl_set_error(const char* fmt, ...);
+
+#define HL_CHECK_ARG(cond, msg)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      hl_set_error("%s: %s", __func__, msg); \
+      return HL_E_INVALID;               \
+    }                                    \
+  } while (0)
+
+#define HL_CHECK_LAUNCH()                                                        \
+  do {                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    if (e__ != cudaSuccess) {                                                    \
+      hl_set_error("%s: CUDA error: %s", __func__, cudaGetErrorString(e__));     \
+      return HL_E_CUDA;                                                          \
+    }                                                                            \
+  } while (0)
+
+// ----------------------------------------------------------------------------- reward term ids
+// sorted() order of the 51 unique `_reward_*` names (legged_robot.py:1444-1770); mirrored by
+// isaacgymloco_b200/config.py::REWARD_TERMS.
+enum HlTerm : int {
+  T_action_rate = 0, T_ang_vel_xy, T_ang_vel_xy_up, T_base_height, T_base_height_up, T_calf_pose,
+  T_calf_pose_up, T_collision, T_collision_up, T_dof_acc, T_dof_pos_dif, T_dof_pos_limits,
+  T_dof_vel, T_dof_vel_limits, T_feet_air_time, T_feet_contact_forces, T_feet_mirror,
+  T_feet_mirror_up, T_feet_slide, T_feet_slide_up, T_feet_stumble, T_feet_stumble_up,
+  T_foot_clearance_base, T_foot_clearance_base_up, T_foot_clearance_terrain,
+  T_foot_clearance_terrain_up, T_has_contact, T_hip_action_magnitude, T_hip_pos, T_hip_pos_up,
+  T_joint_power, T_lin_vel_z, T_lin_vel_z_up, T_orientation, T_orientation_up, T_power,
+  T_power_distribution, T_smoothness, T_stand_nice, T_stand_still, T_stuck, T_termination,
+  T_thigh_pose, T_thigh_pose_up, T_torque_limits, T_torques, T_torques_dif,
+  T_torques_distribution, T_tracking_ang_vel, T_tracking_lin_vel, T_upward, T_COUNT
+};
+
+// ----------------------------------------------------------------------------- Philox4x32-10
+// Counter-based RNG for the throughput-mode observation noise (the reference draws it with
+// torch.rand_like, LR:394,400,451,457, whose CUDA generator is the same Philox family; the
+// streams are statistically, not bitwise, equivalent -- parity tests pass pre-drawn tensors).
+__device__ __forceinline__ uint4 hl_philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float hl_u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// one Philox block = 4 uniforms for (env, block index, stream, step)
+__device__ __forceinline__ uint4 hl_noise_block(uint64_t seed, uint64_t offset, uint64_t env,
+                                                uint32_t block, uint32_t stream) {
+  const uint4 ctr = make_uint4(block | (stream << 24), (uint32_t)env, (uint32_t)(env >> 32) ^ (uint32_t)(offset >> 32),
+                               (uint32_t)offset);
+  return hl_philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+__device__ __forceinline__ float hl_clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// torch `%` on floats (Python sign): fmod then fix-up.
+__device__ __forceinline__ float hl_pymod(float a, float b) {
+  float r = fmodf(a, b);
+  if (r != 0.0f && ((r < 0.0f) != (b < 0.0f))) r += b;
+  return r;
+}

@@ -1,0 +1,870 @@
+// Post-physics kernels (sm_100a): PD torques, the fused post-physics step, the generic
+// per-stage kernel behind the individual drop-in methods, reset-id compaction, terminal rows.
+// Reference: legged_gym/legged_gym/envs/base/legged_robot.py (LR) -- see include/himloco_b200.h.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "hl_math.cuh"
+
+// ----------------------------------------------------------------------------- error string
+static thread_local char g_err[512] = "";
+void hl_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* hl_last_error(void) { return g_err; }
+extern "C" int hl_version(void) { return HL_VERSION; }
+extern "C" int hl_sizeof_cfg(void) { return (int)sizeof(HlCfg); }
+extern "C" int hl_sizeof_env_buffers(void) { return (int)sizeof(HlEnvBuffers); }
+
+static int check_cfg(const HlCfg* c, const HlEnvBuffers* b) {
+  if (!c || c->struct_bytes != (int)sizeof(HlCfg)) {
+    hl_set_error("HlCfg size mismatch (binding %d vs library %d)", c ? c->struct_bytes : -1, (int)sizeof(HlCfg));
+    return HL_E_INVALID;
+  }
+  if (b && b->struct_bytes != (int)sizeof(HlEnvBuffers)) {
+    hl_set_error("HlEnvBuffers size mismatch (binding %d vs library %d)", b->struct_bytes, (int)sizeof(HlEnvBuffers));
+    return HL_E_INVALID;
+  }
+  if (c->n_terms < 0 || c->n_terms > HL_MAX_TERMS || c->n_px > HL_MAX_PTS || c->n_py > HL_MAX_PTS ||
+      c->n_px * c->n_py > 256 || c->n_bx * c->n_by > 256 || c->num_bodies < 1 || c->n_penalised > HL_MAX_BODIES_IDX ||
+      c->n_term_contact > HL_MAX_BODIES_IDX) {
+    hl_set_error("HlCfg out of range");
+    return HL_E_INVALID;
+  }
+  return HL_OK;
+}
+
+// ============================================================================= a1: PD torques
+// LR:658-688.  One thread per (env, dof); dof_state read as float2 (pos, vel).
+__global__ void __launch_bounds__(256) hl_pd_torque_kernel(HlCfg c, const float* __restrict__ actions, long long a_stride,
+                                                           const float2* __restrict__ dof_state,
+                                                           const float* __restrict__ motor_strength,
+                                                           const float* __restrict__ kp, const float* __restrict__ kd,
+                                                           const float* __restrict__ last_dof_vel,
+                                                           float* __restrict__ out, float* __restrict__ target_out,
+                                                           long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long e = i / 12;
+  const int d = (int)(i - e * 12);
+  const float a = motor_strength[i] * actions[e * a_stride + d];
+  float scaled = a * c.action_scale;
+  if (d % 3 == 0) scaled *= c.hip_reduction;  // columns [0,3,6,9]
+  const float target = c.default_dof_pos[d] + scaled;
+  const float2 pv = dof_state[i];
+  float tq;
+  if (c.control_type == 0) {
+    tq = c.p_gains[d] * kp[e] * (target - pv.x) - c.d_gains[d] * kd[e] * pv.y;
+  } else if (c.control_type == 1) {
+    tq = c.p_gains[d] * (scaled - pv.y) - c.d_gains[d] * (pv.y - last_dof_vel[i]) / c.sim_dt;
+  } else {
+    tq = scaled;
+  }
+  out[i] = hl_clampf(tq, -c.torque_limits[d], c.torque_limits[d]);
+  if (target_out) target_out[i] = target;
+}
+
+extern "C" int hl_pd_torque(const HlCfg* cfg, const float* actions, int64_t a_stride, const float* dof_state,
+                            const float* motor_strength, const float* kp, const float* kd, const float* last_dof_vel,
+                            float* torques_out, float* target_out, int64_t n, void* stream) {
+  if (int r = check_cfg(cfg, nullptr)) return r;
+  HL_CHECK_ARG(actions && dof_state && motor_strength && kp && kd && torques_out, "null pointer");
+  HL_CHECK_ARG(cfg->control_type != 1 || last_dof_vel, "control_type V needs last_dof_vel");
+  if (n <= 0) return HL_OK;
+  const long long total = n * 12;
+  hl_pd_torque_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      *cfg, actions, a_stride, (const float2*)dof_state, motor_strength, kp, kd, last_dof_vel, torques_out, target_out, total);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}
+
+// ============================================================================= terrain min3 table
+__global__ void hl_terrain_min3_kernel(const int16_t* __restrict__ h, int rows, int cols, int16_t* __restrict__ out) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x, x = blockIdx.y;
+  if (y >= cols - 1 || x >= rows - 1) return;
+  const int a = h[(size_t)x * cols + y], b = h[(size_t)(x + 1) * cols + y], c = h[(size_t)x * cols + y + 1];
+  out[(size_t)x * (cols - 1) + y] = (int16_t)min(min(a, b), c);
+}
+extern "C" int hl_terrain_prepare(const int16_t* hs, int32_t rows, int32_t cols, int16_t* out, void* stream) {
+  HL_CHECK_ARG(hs && out && rows >= 2 && cols >= 2, "bad terrain");
+  dim3 grid((cols - 1 + 255) / 256, rows - 1);
+  hl_terrain_min3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(hs, rows, cols, out);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}
+
+// ============================================================================= shared pieces
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Noise for 32 consecutive height points per iteration out of one Philox pass per 4 iterations:
+// in pass a, lane l owns block (a*32 + l) = uniforms for points 128a + 4l .. 4l+3; iteration
+// it = 4a + c needs, for point 32 it + l, component (l & 3) of the block held by lane 8c + l/4.
+struct HeightNoise {
+  uint4 blk;
+  __device__ __forceinline__ void refill(const HlEnvBuffers& b, unsigned long long genv, int pass, int lane, unsigned stream) {
+    blk = hl_noise_block(b.philox_seed, b.philox_offset, genv, (unsigned)(pass * 32 + lane), stream);
+  }
+  __device__ __forceinline__ float get(int it, int lane) const {
+    const int src = ((it & 3) << 3) + (lane >> 2);
+    const unsigned x = __shfl_sync(0xffffffffu, blk.x, src), y = __shfl_sync(0xffffffffu, blk.y, src);
+    const unsigned z = __shfl_sync(0xffffffffu, blk.z, src), w = __shfl_sync(0xffffffffu, blk.w, src);
+    const int cpt = lane & 3;
+    return hl_u01(cpt == 0 ? x : (cpt == 1 ? y : (cpt == 2 ? z : w)));
+  }
+};
+
+// Warp-cooperative scans for one env.  `root` = the env's 13-float root record.
+// Writes measured_heights (and optionally the height part of privileged_obs + debug indices);
+// returns _get_base_heights() when want_base.
+struct ScanOut {
+  float* measured;     // row of measured_heights or nullptr
+  float* priv_heights; // &privileged_obs[e][51] or nullptr
+  int32_t* idx;        // debug (P,2) or nullptr
+  const float* u187;   // pre-drawn noise row or nullptr
+  bool clip;
+  float* keep;         // optional: lane-private copy of this lane's heights, keep[it]
+};
+
+__device__ __forceinline__ float hl_warp_scan_env(const HlCfg& c, const HlEnvBuffers& b, const float* root,
+                                                  unsigned long long genv, int lane, bool do_heights, bool want_base,
+                                                  const ScanOut& o, unsigned noise_stream) {
+  float qz, qw;
+  hl_yaw_quat(root + 3, qz, qw);
+  const float posx = root[0], posy = root[1], posz = root[2];
+  float base_h = 0.0f;
+  if (do_heights) {
+    const int P = c.n_px * c.n_py;
+    if (c.mesh_type == 0) {  // plane: zeros (LR:1331-1332)
+      HeightNoise hn;
+      for (int it = 0; it * 32 < P; ++it) {
+        const int p = it * 32 + lane;
+        if (o.priv_heights && !o.u187 && (it & 3) == 0) hn.refill(b, genv, it >> 2, lane, noise_stream);
+        float u = 0.5f;
+        if (o.priv_heights && c.add_noise) u = o.u187 ? (p < P ? o.u187[p] : 0.5f) : hn.get(it, lane);
+        if (p < P) {
+          if (o.measured) o.measured[p] = 0.0f;
+          if (o.keep) o.keep[it] = 0.0f;
+          if (o.priv_heights) {
+            float hv = hl_obs_height(c, posz, 0.0f, u);
+            if (o.clip) hv = hl_clampf(hv, -c.clip_obs, c.clip_obs);
+            o.priv_heights[p] = hv;
+          }
+        }
+      }
+    } else {
+      const ScanAxis axi = hl_scan_axis_x(qz, qw, c.px[lane < c.n_px ? lane : 0]);
+      const ScanAxis axj = hl_scan_axis_y(qz, qw, c.py[lane < c.n_py ? lane : 0]);
+      HeightNoise hn;
+      for (int it = 0; it * 32 < P; ++it) {
+        const int p = it * 32 + lane;
+        const int pc = p < P ? p : P - 1;
+        const int i = pc / c.n_py, j = pc - i * c.n_py;
+        ScanAxis ai, aj;
+        ai.a = __shfl_sync(0xffffffffu, axi.a, i);
+        ai.c = __shfl_sync(0xffffffffu, axi.c, i);
+        aj.a = __shfl_sync(0xffffffffu, axj.a, j);
+        aj.c = __shfl_sync(0xffffffffu, axj.c, j);
+        int px, py;
+        const int hraw = hl_scan_point(c, b, posx, posy, c.px[i], c.py[j], ai, aj, &px, &py);
+        const float mh = (float)hraw * c.vertical_scale;
+        if (o.priv_heights && !o.u187 && (it & 3) == 0) hn.refill(b, genv, it >> 2, lane, noise_stream);
+        float u = 0.5f;
+        if (o.priv_heights && c.add_noise) u = o.u187 ? (p < P ? o.u187[p] : 0.5f) : hn.get(it, lane);
+        if (p < P) {
+          if (o.measured) o.measured[p] = mh;
+          if (o.keep) o.keep[it] = mh;
+          if (o.idx) { o.idx[2 * p] = px; o.idx[2 * p + 1] = py; }
+          if (o.priv_heights) {
+            float hv = hl_obs_height(c, posz, mh, u);
+            if (o.clip) hv = hl_clampf(hv, -c.clip_obs, c.clip_obs);
+            o.priv_heights[p] = hv;
+          }
+        }
+      }
+    }
+  }
+  if (want_base) {  // LR:1357-1398
+    if (c.mesh_type == 0) {
+      base_h = posz;
+    } else {
+      const int P = c.n_bx * c.n_by;
+      const ScanAxis axi = hl_scan_axis_x(qz, qw, c.bx[lane < c.n_bx ? lane : 0]);
+      const ScanAxis axj = hl_scan_axis_y(qz, qw, c.by[lane < c.n_by ? lane : 0]);
+      float acc = 0.0f;
+      for (int it = 0; it * 32 < P; ++it) {
+        const int p = it * 32 + lane;
+        const int pc = p < P ? p : P - 1;
+        const int i = pc / c.n_by, j = pc - i * c.n_by;
+        ScanAxis ai, aj;
+        ai.a = __shfl_sync(0xffffffffu, axi.a, i);
+        ai.c = __shfl_sync(0xffffffffu, axi.c, i);
+        aj.a = __shfl_sync(0xffffffffu, axj.a, j);
+        aj.c = __shfl_sync(0xffffffffu, axj.c, j);
+        const int hraw = hl_scan_point(c, b, posx, posy, c.bx[i], c.by[j], ai, aj, nullptr, nullptr);
+        if (p < P) acc += posz - (float)hraw * c.vertical_scale;
+      }
+      base_h = warp_sum(acc) / (float)P;
+    }
+  }
+  return base_h;
+}
+
+__device__ __forceinline__ int hl_priv_dim(const HlCfg& c) { return 51 + (c.measure_heights ? c.n_px * c.n_py : 0); }
+
+// ============================================================================= generic stage kernel
+// One warp per env (optionally per listed env id); scalars are computed redundantly by all lanes,
+// vector work (scan, obs rows) is lane-parallel.  Serves the individual drop-in methods and the
+// post-reset fix-up; the hot path is hl_post_physics_fused_kernel below.
+__global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, unsigned stages,
+                                                       const long long* __restrict__ ids,
+                                                       const int* __restrict__ n_ids, long long n) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long items = ids ? (long long)*n_ids : n;
+  const int B = c.num_bodies;
+  const int P = c.n_px * c.n_py;
+  const int PD = hl_priv_dim(c);
+  for (long long it0 = warp0; it0 < items; it0 += nwarps) {
+    const long long e = ids ? ids[it0] : it0;
+    if (e < 0 || e >= n) continue;
+    EnvView v;
+    v.root = b.root_states + e * 13;
+    v.dof = b.dof_state + e * 24;
+    v.cf = b.contact_forces + e * B * 3;
+    for (int f = 0; f < 4; ++f) v.foot[f] = b.rigid_body_states + (e * B + c.feet_idx[f]) * 13;
+    v.act = b.actions + e * 12;
+    v.lact = b.last_actions + e * 12;
+    v.llact = b.last_last_actions + e * 12;
+    v.ldp = b.last_dof_pos + e * 12;
+    v.ldv = b.last_dof_vel + e * 12;
+    v.tq = b.torques + e * 12;
+    v.ltq = b.last_torques + e * 12;
+    EnvScalars s;
+    s.gid = e + c.env_id_offset;
+    s.feet_shift = 0;
+    s.base_h = 0.0f;
+    s.terrain_level = b.terrain_levels ? b.terrain_levels[e] : 0;
+    s.ep_len = b.episode_length_buf[e];
+    for (int k = 0; k < 4; ++k) s.cmd[k] = b.commands[e * 4 + k];
+    for (int k = 0; k < 4; ++k) s.air[k] = b.feet_air_time[e * 4 + k];
+    unsigned last = 0, filt = 0;
+    for (int f = 0; f < 4; ++f) {
+      last |= (b.last_contacts[e * 4 + f] ? 1u : 0u) << f;
+      filt |= (b.contact_filt[e * 4 + f] ? 1u : 0u) << f;
+    }
+    s.last_contact = last;
+    s.cfilt = filt;
+    s.contact = 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) s.contact |= (v.cf[c.feet_idx[f] * 3 + 2] > 1.0f ? 1u : 0u) << f;
+    s.reset = b.reset_buf[e] != 0;
+    s.time_out = b.time_out_buf[e] != 0;
+    __syncwarp();
+
+    if (stages & HL_ST_COUNTERS) {
+      s.ep_len += 1;
+      if (lane == 0) b.episode_length_buf[e] = s.ep_len;
+    }
+    if (stages & HL_ST_FRAME) {
+      hl_frame(v, s);
+      if (lane < 3) {
+        b.base_lin_vel[e * 3 + lane] = s.blv[lane];
+        b.base_ang_vel[e * 3 + lane] = s.bav[lane];
+        b.projected_gravity[e * 3 + lane] = s.pg[lane];
+      }
+    } else {
+      for (int k = 0; k < 3; ++k) {
+        s.blv[k] = b.base_lin_vel[e * 3 + k];
+        s.bav[k] = b.base_ang_vel[e * 3 + k];
+        s.pg[k] = b.projected_gravity[e * 3 + k];
+      }
+    }
+    if (stages & HL_ST_CONTACTS) {
+      hl_contacts(c, v, last, s);
+      if (lane < 4) {
+        b.contact_filt[e * 4 + lane] = (s.cfilt >> lane) & 1u;
+        b.last_contacts[e * 4 + lane] = (s.last_contact >> lane) & 1u;
+      }
+      if (lane < 12) {
+        const int f = lane / 3, k = lane % 3;
+        if (b.feet_pos) b.feet_pos[e * 12 + lane] = v.foot[f][k];
+        if (b.feet_vel) b.feet_vel[e * 12 + lane] = v.foot[f][7 + k];
+      }
+    }
+    if ((stages & HL_ST_HEADING) && c.heading_command) {
+      s.cmd[2] = hl_heading_command(v.root + 3, s.cmd[3]);
+      if (lane == 0) b.commands[e * 4 + 2] = s.cmd[2];
+    }
+    float myh[8];
+    const bool do_h = (stages & HL_ST_HEIGHTS) && c.measure_heights;
+    const bool want_base = ((stages & HL_ST_REWARD) && hl_needs_base_height(c)) || (stages & HL_ST_BASE_HEIGHT);
+    if (do_h || want_base) {
+      ScanOut o;
+      o.measured = b.measured_heights + e * P;
+      o.priv_heights = nullptr;
+      o.idx = b.height_idx_out ? b.height_idx_out + e * P * 2 : nullptr;
+      o.u187 = nullptr;
+      o.clip = false;
+      o.keep = myh;
+      s.base_h = hl_warp_scan_env(c, b, v.root, (unsigned long long)s.gid, lane, do_h, want_base, o, 0u);
+      if ((stages & HL_ST_BASE_HEIGHT) && b.base_height_out && lane == 0) b.base_height_out[e] = s.base_h;
+    }
+    if (stages & HL_ST_TERMINATION) {
+      hl_check_termination(c, v, s);
+      if (lane == 0) {
+        b.reset_buf[e] = s.reset;
+        b.time_out_buf[e] = s.time_out;
+      }
+    }
+    if (stages & HL_ST_REWARD) {
+      const float rew = hl_compute_reward(c, b, v, s, b.episode_sums ? b.episode_sums + e : nullptr, n, lane == 0);
+      if (lane == 0) b.rew_buf[e] = rew;
+      if (lane < 4) {
+        b.feet_air_time[e * 4 + lane] = s.air[lane];
+        b.last_contacts[e * 4 + lane] = (s.last_contact >> lane) & 1u;
+      }
+    }
+    if (stages & HL_ST_OBS) {
+      const bool clip = stages & HL_ST_OBS_CLIP;
+      const float cl = c.clip_obs;
+      // history first (registers), then the new slot: safe when obs_buf_out aliases obs_buf_in
+      float old[8];
+      if (!(stages & HL_ST_OBS_NOSHIFT)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = i * 32 + lane;
+          old[i] = k < 225 ? b.obs_buf_in[e * 270 + k] : 0.0f;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = i * 32 + lane;
+          if (k < 225) b.obs_buf_out[e * 270 + 45 + k] = clip ? hl_clampf(old[i], -cl, cl) : old[i];
+        }
+      }
+      for (int k = lane; k < 45; k += 32) {
+        float u = 0.5f;
+        if (c.add_noise) {
+          if (b.noise_u45) u = b.noise_u45[e * 45 + k];
+          else {
+            const uint4 r = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)s.gid, (unsigned)(k >> 2), 2u);
+            const int cpt = k & 3;
+            u = hl_u01(cpt == 0 ? r.x : (cpt == 1 ? r.y : (cpt == 2 ? r.z : r.w)));
+          }
+        }
+        float x = hl_add_noise45(c, hl_obs45(c, v, s, k), u, k);
+        if (clip) x = hl_clampf(x, -cl, cl);
+        b.obs_buf_out[e * 270 + k] = x;
+        b.privileged_obs_buf[e * PD + k] = x;
+      }
+      if (lane < 6) {
+        float x = lane < 3 ? s.blv[lane] * c.obs_lin_vel : b.disturbance[e * B * 3 + (lane - 3)];
+        if (clip) x = hl_clampf(x, -cl, cl);
+        b.privileged_obs_buf[e * PD + 45 + lane] = x;
+      }
+      if (c.measure_heights) {
+        HeightNoise hn;
+        const float rz = v.root[2];
+        for (int it = 0; it * 32 < P; ++it) {
+          const int p = it * 32 + lane;
+          if (!b.noise_u187 && (it & 3) == 0) hn.refill(b, (unsigned long long)s.gid, it >> 2, lane, 0u);
+          float u = 0.5f;
+          if (c.add_noise) u = b.noise_u187 ? (p < P ? b.noise_u187[e * P + p] : 0.5f) : hn.get(it, lane);
+          if (p < P) {
+            const float mh = do_h ? myh[it] : b.measured_heights[e * P + p];
+            float hv = hl_obs_height(c, rz, mh, u);
+            if (clip) hv = hl_clampf(hv, -cl, cl);
+            b.privileged_obs_buf[e * PD + 51 + p] = hv;
+          }
+        }
+      }
+    }
+    if (stages & HL_ST_ROLL) {  // LR:235-241 (reads complete before writes: llact <- lact <- act)
+      __syncwarp();
+      float la = 0.f, a = 0.f, dp = 0.f, dv = 0.f, tq = 0.f, rv = 0.f;
+      if (lane < 12) {
+        la = v.lact[lane];
+        a = v.act[lane];
+        dp = v.dof_pos(lane);
+        dv = v.dof_vel(lane);
+        tq = v.tq[lane];
+      }
+      if (lane < 6) rv = v.root[7 + lane];
+      __syncwarp();
+      if (lane < 12) {
+        b.last_last_actions[e * 12 + lane] = la;
+        b.last_actions[e * 12 + lane] = a;
+        b.last_dof_pos[e * 12 + lane] = dp;
+        b.last_dof_vel[e * 12 + lane] = dv;
+        b.last_torques[e * 12 + lane] = tq;
+      }
+      if (lane < 6) b.last_root_vel[e * 6 + lane] = rv;
+      if (lane < 3) b.disturbance[e * B * 3 + lane] = 0.0f;
+    }
+  }
+}
+
+static int launch_stage(const HlCfg* cfg, const HlEnvBuffers* bufs, unsigned stages, const int64_t* ids,
+                        const int32_t* n_ids, int64_t n, void* stream) {
+  if (int r = check_cfg(cfg, bufs)) return r;
+  HL_CHECK_ARG((ids == nullptr) == (n_ids == nullptr), "env_ids and n_ids_dev go together");
+  if (n <= 0) return HL_OK;
+  long long blocks = (n * 32 + 255) / 256;
+  if (ids) blocks = blocks < 148 * 4 ? blocks : 148 * 4;  // id lists are short; grid-stride covers the rest
+  hl_stage_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*cfg, *bufs, stages, (const long long*)ids, n_ids, n);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}
+
+extern "C" int hl_post_physics_stages(const HlCfg* cfg, const HlEnvBuffers* bufs, uint32_t stages,
+                                      const int64_t* env_ids, const int32_t* n_ids_dev, int64_t n, void* stream) {
+  return launch_stage(cfg, bufs, stages, env_ids, n_ids_dev, n, stream);
+}
+
+extern "C" int hl_post_reset_fixup(const HlCfg* cfg, const HlEnvBuffers* bufs, const int64_t* env_ids,
+                                   const int32_t* n_ids_dev, int64_t n, void* stream) {
+  HL_CHECK_ARG(env_ids && n_ids_dev, "needs the reset id list");
+  return launch_stage(cfg, bufs, HL_ST_HEIGHTS | HL_ST_OBS | HL_ST_OBS_NOSHIFT | HL_ST_OBS_CLIP | HL_ST_ROLL, env_ids,
+                      n_ids_dev, n, stream);
+}
+
+// ============================================================================= terminal rows
+// compute_termination_observations(env_ids) + get_amp_observations()[env_ids] (LR:227-228):
+// one warp per reset env, from the persisted pre-reset derived state.
+__global__ void __launch_bounds__(256) hl_terminal_rows_kernel(HlCfg c, HlEnvBuffers b, const long long* __restrict__ ids,
+                                                               const int* __restrict__ n_ids,
+                                                               const float* __restrict__ u45,
+                                                               const float* __restrict__ u187,
+                                                               float* __restrict__ out_priv, float* __restrict__ out_amp,
+                                                               long long n) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long items = *n_ids;
+  const int B = c.num_bodies, P = c.n_px * c.n_py, PD = hl_priv_dim(c);
+  for (long long r = warp0; r < items; r += nwarps) {
+    const long long e = ids[r];
+    if (e < 0 || e >= n) continue;
+    EnvView v;
+    v.root = b.root_states + e * 13;
+    v.dof = b.dof_state + e * 24;
+    v.act = b.actions + e * 12;
+    EnvScalars s;
+    s.gid = e + c.env_id_offset;
+    for (int k = 0; k < 4; ++k) s.cmd[k] = b.commands[e * 4 + k];
+    for (int k = 0; k < 3; ++k) {
+      s.blv[k] = b.base_lin_vel[e * 3 + k];
+      s.bav[k] = b.base_ang_vel[e * 3 + k];
+      s.pg[k] = b.projected_gravity[e * 3 + k];
+    }
+    for (int k = lane; k < 45; k += 32) {
+      float u = 0.5f;
+      if (c.add_noise) {
+        if (u45) u = u45[e * 45 + k];
+        else {
+          const uint4 rr = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)s.gid, (unsigned)(k >> 2), 3u);
+          const int cpt = k & 3;
+          u = hl_u01(cpt == 0 ? rr.x : (cpt == 1 ? rr.y : (cpt == 2 ? rr.z : rr.w)));
+        }
+      }
+      out_priv[r * PD + k] = hl_add_noise45(c, hl_obs45(c, v, s, k), u, k);
+    }
+    if (lane < 6) out_priv[r * PD + 45 + lane] = lane < 3 ? s.blv[lane] * c.obs_lin_vel : b.disturbance[e * B * 3 + (lane - 3)];
+    if (c.measure_heights) {
+      HeightNoise hn;
+      const float rz = v.root[2];
+      for (int it = 0; it * 32 < P; ++it) {
+        const int p = it * 32 + lane;
+        if (!u187 && (it & 3) == 0) hn.refill(b, (unsigned long long)s.gid, it >> 2, lane, 1u);
+        float u = 0.5f;
+        if (c.add_noise) u = u187 ? (p < P ? u187[e * P + p] : 0.5f) : hn.get(it, lane);
+        if (p < P) out_priv[r * PD + 51 + p] = hl_obs_height(c, rz, b.measured_heights[e * P + p], u);
+      }
+    }
+    if (out_amp && lane < 30) {  // LR:416: dof_pos 12, base_lin_vel 3, base_ang_vel 3, dof_vel 12
+      float x;
+      if (lane < 12) x = v.dof_pos(lane);
+      else if (lane < 15) x = s.blv[lane - 12];
+      else if (lane < 18) x = s.bav[lane - 15];
+      else x = v.dof_vel(lane - 18);
+      out_amp[r * 30 + lane] = x;
+    }
+  }
+}
+
+extern "C" int hl_terminal_rows(const HlCfg* cfg, const HlEnvBuffers* bufs, const int64_t* env_ids,
+                                const int32_t* n_ids_dev, const float* u45, const float* u187, float* out_priv,
+                                float* out_amp, int64_t n, void* stream) {
+  if (int r = check_cfg(cfg, bufs)) return r;
+  HL_CHECK_ARG(env_ids && n_ids_dev && out_priv, "null pointer");
+  if (n <= 0) return HL_OK;
+  hl_terminal_rows_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(*cfg, *bufs, (const long long*)env_ids, n_ids_dev, u45,
+                                                                 u187, out_priv, out_amp, n);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}
+
+// ============================================================================= a13: AMP observations
+__global__ void __launch_bounds__(256) hl_amp_obs_kernel(const float* __restrict__ dof, const float* __restrict__ blv,
+                                                         const float* __restrict__ bav, float* __restrict__ out,
+                                                         long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long e = i / 30;
+  const int k = (int)(i - e * 30);
+  float x;
+  if (k < 12) x = dof[e * 24 + 2 * k];
+  else if (k < 15) x = blv[e * 3 + (k - 12)];
+  else if (k < 18) x = bav[e * 3 + (k - 15)];
+  else x = dof[e * 24 + 2 * (k - 18) + 1];
+  out[i] = x;
+}
+extern "C" int hl_amp_observations(const float* dof_state, const float* blv, const float* bav, float* out, int64_t n,
+                                   void* stream) {
+  HL_CHECK_ARG(dof_state && blv && bav && out, "null pointer");
+  if (n <= 0) return HL_OK;
+  const long long total = n * 30;
+  hl_amp_obs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dof_state, blv, bav, out, total);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}
+
+// ============================================================================= a10: reset ids
+// env_ids = reset_buf.nonzero().flatten() (LR:225): ordered stream compaction.  One CTA walks the
+// flags 16 KB at a time (uint4 per thread), warp-shuffle scan inside, running offset across
+// chunks.  N bytes of input: ~4 chunks at 65,536 envs.
+__global__ void __launch_bounds__(1024) hl_select_ids_kernel(const uint8_t* __restrict__ flags, long long n,
+                                                             long long* __restrict__ ids, int* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int running_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) running_s = 0;
+  __syncthreads();
+  const bool aligned = ((uintptr_t)flags & 15) == 0;
+  for (long long base = 0; base < n; base += 1024 * 16) {
+    const long long off = base + (long long)tid * 16;
+    unsigned mask = 0;
+    if (off + 16 <= n && aligned) {
+      const uint4 q = *reinterpret_cast<const uint4*>(flags + off);
+      const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mask |= (((w[k] >> (8 * j)) & 0xffu) ? 1u : 0u) << (4 * k + j);
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (off + j < n && flags[off + j]) mask |= 1u << j;
+    }
+    const int cnt = __popc(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    const int running = running_s;
+    if (wid == 0) {
+      int wt = warp_tot[lane], wi = wt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_tot[lane] = wi - wt;  // exclusive prefix of warp totals
+      if (lane == 31) running_s = running + wi;
+    }
+    __syncthreads();
+    int pos = running + warp_tot[wid] + incl - cnt;
+    while (mask) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      ids[pos++] = off + j;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *count = running_s;
+}
+extern "C" int64_t hl_select_workspace_bytes(int64_t) { return 256; }
+extern "C" int hl_select_reset_ids(const uint8_t* reset_buf, int64_t n, int64_t* ids_out, int32_t* count_out, void*,
+                                   void* stream) {
+  HL_CHECK_ARG(reset_buf && ids_out && count_out && n >= 0, "null pointer");
+  hl_select_ids_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(reset_buf, n, (long long*)ids_out, count_out);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}
+
+// ============================================================================= the fused step
+// One CTA = EPB consecutive envs.
+//   phase 0  coalesced slab loads of every AoS record into shared memory (odd row strides);
+//   phase 1  height scans, one warp per env: 187-point grid -> measured_heights + the height part
+//            of privileged_obs (noise fused), 63-point base grid -> base height;
+//   phase 2  one lane per env: frame, contacts, heading, termination, rewards, one-step obs;
+//   phase 3  coalesced stores: obs history shift (register-staged, in-place safe), slot 0,
+//            privileged_obs[0:51], the last_* roll.
+constexpr int EPB = 64;
+constexpr int FUSED_THREADS = 256;
+constexpr int S13 = 13, SDOF = 25, SFOOT = 53, SCUR = 51;
+
+struct FusedSmem {
+  float root[EPB * S13];
+  float dof[EPB * SDOF];
+  float foot[EPB * SFOOT];
+  float act[EPB * S13], lact[EPB * S13], llact[EPB * S13], ldp[EPB * S13], ldv[EPB * S13], tq[EPB * S13], ltq[EPB * S13];
+  float cur[EPB * SCUR];
+  float base_h[EPB];
+  unsigned char reset[EPB];
+  // contact forces follow (EPB * cf_stride floats), sized at launch
+};
+
+// global (count x rec contiguous) -> shared rows of `stride`
+__device__ __forceinline__ void stage_in(float* dst, int stride, const float* __restrict__ src, int rec, int count, int tid) {
+  const int total = count * rec;
+  int e = tid / rec, k = tid - e * rec;
+  const int de = FUSED_THREADS / rec, dk = FUSED_THREADS - de * rec;
+  for (int i = tid; i < total; i += FUSED_THREADS) {
+    dst[e * stride + k] = __ldg(src + i);
+    e += de;
+    k += dk;
+    if (k >= rec) { k -= rec; ++e; }
+  }
+}
+// shared rows -> global (count x rec contiguous); rows whose env resets are left to the
+// post-reset fix-up (hl_post_reset_fixup), which redoes the roll after reset_idx ran
+__device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* src, int stride, int rec, int count, int tid,
+                                          const unsigned char* skip) {
+  const int total = count * rec;
+  int e = tid / rec, k = tid - e * rec;
+  const int de = FUSED_THREADS / rec, dk = FUSED_THREADS - de * rec;
+  for (int i = tid; i < total; i += FUSED_THREADS) {
+    if (!skip[e]) dst[i] = src[e * stride + k];
+    e += de;
+    k += dk;
+    if (k >= rec) { k -= rec; ++e; }
+  }
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS) hl_post_physics_fused_kernel(HlCfg c, HlEnvBuffers b, long long n,
+                                                                              int cf_stride, int need_ldp, int need_ltq) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
+  float* s_cf = reinterpret_cast<float*>(smem_raw + sizeof(FusedSmem));
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long e0 = (long long)blockIdx.x * EPB;
+  const int cnt = (int)((n - e0) < EPB ? (n - e0) : EPB);
+  const int B = c.num_bodies, P = c.n_px * c.n_py, PD = hl_priv_dim(c);
+
+  // ---------------- phase 0: stage inputs
+  stage_in(sm.root, S13, b.root_states + e0 * 13, 13, cnt, tid);
+  stage_in(sm.dof, SDOF, b.dof_state + e0 * 24, 24, cnt, tid);
+  stage_in(s_cf, cf_stride, b.contact_forces + e0 * B * 3, B * 3, cnt, tid);
+  for (int i = tid; i < cnt * 52; i += FUSED_THREADS) {
+    const int e = i / 52, r = i - e * 52, f = r / 13, k = r - f * 13;
+    sm.foot[e * SFOOT + r] = __ldg(b.rigid_body_states + ((e0 + e) * B + c.feet_idx[f]) * 13 + k);
+  }
+  stage_in(sm.act, S13, b.actions + e0 * 12, 12, cnt, tid);
+  stage_in(sm.lact, S13, b.last_actions + e0 * 12, 12, cnt, tid);
+  stage_in(sm.llact, S13, b.last_last_actions + e0 * 12, 12, cnt, tid);
+  stage_in(sm.ldv, S13, b.last_dof_vel + e0 * 12, 12, cnt, tid);
+  stage_in(sm.tq, S13, b.torques + e0 * 12, 12, cnt, tid);
+  if (need_ldp) stage_in(sm.ldp, S13, b.last_dof_pos + e0 * 12, 12, cnt, tid);
+  if (need_ltq) stage_in(sm.ltq, S13, b.last_torques + e0 * 12, 12, cnt, tid);
+  __syncthreads();
+
+  // ---------------- phase 1: height scans (warp per env)
+  const bool want_base = hl_needs_base_height(c);
+  for (int e = wid; e < cnt; e += FUSED_THREADS / 32) {
+    const long long ge = e0 + e;
+    ScanOut o;
+    o.measured = b.measured_heights + ge * P;
+    o.priv_heights = b.privileged_obs_buf + ge * PD + 51;
+    o.idx = nullptr;
+    o.u187 = b.noise_u187 ? b.noise_u187 + ge * P : nullptr;
+    o.clip = true;
+    o.keep = nullptr;
+    const float bh = hl_warp_scan_env(c, b, sm.root + e * S13, (unsigned long long)(ge + c.env_id_offset), lane,
+                                      c.measure_heights != 0, want_base, o, 0u);
+    if (lane == 0) sm.base_h[e] = bh;
+  }
+  __syncthreads();
+
+  // ---------------- phase 2: one lane per env
+  if (tid < cnt) {
+    const int e = tid;
+    const long long ge = e0 + e;
+    EnvView v;
+    v.root = sm.root + e * S13;
+    v.dof = sm.dof + e * SDOF;
+    v.cf = s_cf + e * cf_stride;
+    for (int f = 0; f < 4; ++f) v.foot[f] = sm.foot + e * SFOOT + f * 13;
+    v.act = sm.act + e * S13;
+    v.lact = sm.lact + e * S13;
+    v.llact = sm.llact + e * S13;
+    v.ldp = sm.ldp + e * S13;
+    v.ldv = sm.ldv + e * S13;
+    v.tq = sm.tq + e * S13;
+    v.ltq = sm.ltq + e * S13;
+    EnvScalars s;
+    s.gid = ge + c.env_id_offset;
+    s.feet_shift = 0;
+    s.base_h = sm.base_h[e];
+    s.terrain_level = b.terrain_levels ? b.terrain_levels[ge] : 0;
+    s.ep_len = b.episode_length_buf[ge] + 1;  // LR:193
+    const float4 cm = reinterpret_cast<const float4*>(b.commands)[ge];
+    s.cmd[0] = cm.x; s.cmd[1] = cm.y; s.cmd[2] = cm.z; s.cmd[3] = cm.w;
+    const float4 ar = reinterpret_cast<const float4*>(b.feet_air_time)[ge];
+    s.air[0] = ar.x; s.air[1] = ar.y; s.air[2] = ar.z; s.air[3] = ar.w;
+    const unsigned lc4 = reinterpret_cast<const unsigned*>(b.last_contacts)[ge];
+    unsigned last = 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) last |= (((lc4 >> (8 * f)) & 0xffu) ? 1u : 0u) << f;
+    hl_frame(v, s);
+    hl_contacts(c, v, last, s);
+    if (c.heading_command) s.cmd[2] = hl_heading_command(v.root + 3, s.cmd[3]);
+    hl_check_termination(c, v, s);
+    const float rew = hl_compute_reward(c, b, v, s, b.episode_sums ? b.episode_sums + ge : nullptr, n, true);
+
+    b.episode_length_buf[ge] = s.ep_len;
+    b.commands[ge * 4 + 2] = s.cmd[2];
+    b.reset_buf[ge] = s.reset;
+    b.time_out_buf[ge] = s.time_out;
+    b.rew_buf[ge] = rew;
+    sm.reset[e] = s.reset;
+    unsigned cf4 = 0, lc = 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      cf4 |= ((s.cfilt >> f) & 1u) << (8 * f);
+      lc |= ((s.last_contact >> f) & 1u) << (8 * f);
+    }
+    reinterpret_cast<unsigned*>(b.contact_filt)[ge] = cf4;
+    reinterpret_cast<unsigned*>(b.last_contacts)[ge] = lc;
+    reinterpret_cast<float4*>(b.feet_air_time)[ge] = make_float4(s.air[0], s.air[1], s.air[2], s.air[3]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      b.base_lin_vel[ge * 3 + k] = s.blv[k];
+      b.base_ang_vel[ge * 3 + k] = s.bav[k];
+      b.projected_gravity[ge * 3 + k] = s.pg[k];
+    }
+    // one-step observation (+noise), clipped: LR:385-394,167-171
+    float* cur = sm.cur + e * SCUR;
+    const float cl = c.clip_obs;
+    if (c.add_noise && !b.noise_u45) {
+      for (int kb = 0; kb < 12; ++kb) {
+        const uint4 r = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)s.gid, (unsigned)kb, 2u);
+        const unsigned rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = kb * 4 + j;
+          if (k < 45) cur[k] = hl_clampf(hl_add_noise45(c, hl_obs45(c, v, s, k), hl_u01(rr[j]), k), -cl, cl);
+        }
+      }
+    } else {
+      for (int k = 0; k < 45; ++k) {
+        const float u = (c.add_noise && b.noise_u45) ? b.noise_u45[ge * 45 + k] : 0.5f;
+        cur[k] = hl_clampf(hl_add_noise45(c, hl_obs45(c, v, s, k), u, k), -cl, cl);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      cur[45 + k] = hl_clampf(s.blv[k] * c.obs_lin_vel, -cl, cl);
+      float* dptr = b.disturbance + ge * B * 3 + k;
+      cur[48 + k] = hl_clampf(*dptr, -cl, cl);
+      if (!s.reset) *dptr = 0.0f;  // LR:235; reset envs are zeroed by the post-reset fix-up, which still reads it
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 3: stores
+  for (int e = wid; e < cnt; e += FUSED_THREADS / 32) {
+    const long long ge = e0 + e;
+    const float* src = b.obs_buf_in + ge * 270;
+    float* dst = b.obs_buf_out + ge * 270;
+    float old[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = i * 32 + lane;
+      old[i] = k < 225 ? src[k] : 0.0f;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = i * 32 + lane;
+      if (k < 225) dst[45 + k] = hl_clampf(old[i], -c.clip_obs, c.clip_obs);  // LR:168 clips the whole buffer
+    }
+    const float* cur = sm.cur + e * SCUR;
+    float* priv = b.privileged_obs_buf + ge * PD;
+    for (int k = lane; k < 51; k += 32) {
+      const float x = cur[k];
+      if (k < 45) dst[k] = x;
+      priv[k] = x;
+    }
+  }
+  // end-of-step roll (LR:235-241) for the envs that do not reset
+  stage_out(b.last_last_actions + e0 * 12, sm.lact, S13, 12, cnt, tid, sm.reset);
+  stage_out(b.last_actions + e0 * 12, sm.act, S13, 12, cnt, tid, sm.reset);
+  stage_out(b.last_torques + e0 * 12, sm.tq, S13, 12, cnt, tid, sm.reset);
+  for (int i = tid; i < cnt * 12; i += FUSED_THREADS) {
+    const int e = i / 12, d = i - e * 12;
+    if (sm.reset[e]) continue;
+    b.last_dof_pos[e0 * 12 + i] = sm.dof[e * SDOF + 2 * d];
+    b.last_dof_vel[e0 * 12 + i] = sm.dof[e * SDOF + 2 * d + 1];
+  }
+  for (int i = tid; i < cnt * 6; i += FUSED_THREADS) {
+    const int e = i / 6, k = i - e * 6;
+    if (sm.reset[e]) continue;
+    b.last_root_vel[e0 * 6 + i] = sm.root[e * S13 + 7 + k];
+  }
+  if (b.feet_pos || b.feet_vel) {
+    for (int i = tid; i < cnt * 12; i += FUSED_THREADS) {
+      const int e = i / 12, r = i - e * 12, f = r / 3, k = r - f * 3;
+      if (b.feet_pos) b.feet_pos[e0 * 12 + i] = sm.foot[e * SFOOT + f * 13 + k];
+      if (b.feet_vel) b.feet_vel[e0 * 12 + i] = sm.foot[e * SFOOT + f * 13 + 7 + k];
+    }
+  }
+}
+
+extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, void* stream) {
+  if (int r = check_cfg(cfg, bufs)) return r;
+  const HlEnvBuffers& b = *bufs;
+  HL_CHECK_ARG(b.root_states && b.dof_state && b.contact_forces && b.rigid_body_states && b.actions && b.last_actions &&
+                   b.last_last_actions && b.last_dof_pos && b.last_dof_vel && b.torques && b.last_torques &&
+                   b.last_root_vel && b.commands && b.episode_length_buf && b.last_contacts && b.contact_filt &&
+                   b.feet_air_time && b.disturbance && b.base_lin_vel && b.base_ang_vel && b.projected_gravity &&
+                   b.measured_heights && b.reset_buf && b.time_out_buf && b.rew_buf && b.obs_buf_in && b.obs_buf_out &&
+                   b.privileged_obs_buf,
+               "null buffer");
+  HL_CHECK_ARG(cfg->mesh_type == 0 || b.height_samples || b.height_min3, "terrain table missing");
+  HL_CHECK_ARG(cfg->measure_heights, "the fused step needs measure_heights (privileged obs carries the scan)");
+  if (n <= 0) return HL_OK;
+  int cf_stride = cfg->num_bodies * 3;
+  if ((cf_stride & 1) == 0) cf_stride += 1;
+  int need_ldp = 0, need_ltq = 0;
+  for (int k = 0; k < cfg->n_terms; ++k) {
+    need_ldp |= cfg->term_id[k] == T_dof_pos_dif;
+    need_ltq |= cfg->term_id[k] == T_torques_dif;
+  }
+  const size_t smem = sizeof(FusedSmem) + (size_t)EPB * cf_stride * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(hl_post_physics_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      hl_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return HL_E_CUDA;
+    }
+    attr_set = true;
+  }
+  HL_CHECK_ARG(smem <= 200 * 1024, "num_bodies too large for the shared-memory slab");
+  const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
+  hl_post_physics_fused_kernel<<<blocks, FUSED_THREADS, smem, (cudaStream_t)stream>>>(*cfg, *bufs, n, cf_stride, need_ldp, need_ltq);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}

@@ -1,0 +1,203 @@
+"""AMPLoader: mocap clip tables on the GPU + the batch frame interpolation / expert-pair
+kernels.  Reference: rsl_rl/rsl_rl/datasets/motion_loader.py (ML) -- same class name,
+constructor signature, layout constants and method names.
+
+Load time (JSON parse, leg reorder ML:134-164, per-frame quaternion normalise + standardise
+ML:85-93) stays host-side numpy: it runs once.  Sampling of clip ids / times stays host numpy RNG
+exactly as in the reference (ML:171-187), so a seeded `np.random` yields the reference's stream.
+The per-sample work (`get_full_frame_at_time_batch` ML:231-255, `feed_forward_generator`
+ML:315-343 preload branch) runs in libhimloco_b200.
+"""
+import glob
+import json
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+class AMPLoader:
+    POS_SIZE = 3
+    ROT_SIZE = 4
+    JOINT_POS_SIZE = 12
+    TAR_TOE_POS_LOCAL_SIZE = 12
+    LINEAR_VEL_SIZE = 3
+    ANGULAR_VEL_SIZE = 3
+    JOINT_VEL_SIZE = 12
+    TAR_TOE_VEL_LOCAL_SIZE = 12
+
+    ROOT_POS_START_IDX, ROOT_POS_END_IDX = 0, 3
+    ROOT_ROT_START_IDX, ROOT_ROT_END_IDX = 3, 7
+    JOINT_POSE_START_IDX, JOINT_POSE_END_IDX = 7, 19
+    TAR_TOE_POS_LOCAL_START_IDX, TAR_TOE_POS_LOCAL_END_IDX = 19, 31
+    LINEAR_VEL_START_IDX, LINEAR_VEL_END_IDX = 31, 34
+    ANGULAR_VEL_START_IDX, ANGULAR_VEL_END_IDX = 34, 37
+    JOINT_VEL_START_IDX, JOINT_VEL_END_IDX = 37, 49
+    TAR_TOE_VEL_LOCAL_START_IDX, TAR_TOE_VEL_LOCAL_END_IDX = 49, 61
+
+    def __init__(self, device, time_between_frames, data_dir="", preload_transitions=False,
+                 num_preload_transitions=1000000, motion_files=None, clip_tables=None):
+        """`clip_tables` (optional) = dict(frames=[(n_i,49) arrays], frame_durations=[...],
+        weights=[...], names=[...]) loads pre-parsed clips instead of `motion_files`."""
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("AMPLoader (B200) runs on CUDA only (no CPU fallback)")
+        self.time_between_frames = time_between_frames
+        self.trajectories, self.trajectories_full = [], []
+        self.trajectory_names, self.trajectory_idxs = [], []
+        lens, weights, durations, nframes = [], [], [], []
+        if clip_tables is None:
+            if motion_files is None:
+                motion_files = glob.glob("datasets/motion_files2/*")
+            clip_tables = dict(frames=[], frame_durations=[], weights=[], names=[])
+            for f in motion_files:
+                data, dur, w = self._parse_motion_file(f)
+                clip_tables["frames"].append(data)
+                clip_tables["frame_durations"].append(dur)
+                clip_tables["weights"].append(w)
+                clip_tables["names"].append(f.split(".")[0])
+        for i, frames in enumerate(clip_tables["frames"]):
+            full = torch.as_tensor(np.asarray(frames)[:, :self.JOINT_VEL_END_IDX], dtype=torch.float32).to(self.device)
+            self.trajectories_full.append(full)
+            self.trajectories.append(full[:, self.ROOT_ROT_END_IDX:self.JOINT_VEL_END_IDX])
+            self.trajectory_names.append(clip_tables.get("names", [str(k) for k in range(len(clip_tables["frames"]))])[i])
+            self.trajectory_idxs.append(i)
+            dur = float(clip_tables["frame_durations"][i])
+            durations.append(dur)
+            weights.append(float(clip_tables["weights"][i]))
+            lens.append((full.shape[0] - 1) * dur)             # ML:109 (count-1) * dt
+            nframes.append(float(full.shape[0]))               # ML:111 the frame COUNT
+        self.trajectory_weights = np.array(weights) / np.sum(weights)
+        self.trajectory_frame_durations = np.array(durations)
+        self.trajectory_lens = np.array(lens)
+        self.trajectory_num_frames = np.array(nframes)
+        # one stacked table + per-clip row offsets for the kernels
+        self.all_trajectories_full = torch.vstack(self.trajectories_full).contiguous()
+        offs = np.concatenate([[0], np.cumsum([t.shape[0] for t in self.trajectories_full])[:-1]]).astype(np.int32)
+        self._clip_offset = torch.from_numpy(offs).to(self.device)
+        self._clip_len = torch.from_numpy(self.trajectory_lens.astype(np.float64)).to(self.device)
+        self._clip_nf = torch.from_numpy(self.trajectory_num_frames.astype(np.float64)).to(self.device)
+        self.preload_transitions = preload_transitions
+        if self.preload_transitions:
+            traj_idxs = self.weighted_traj_idx_sample_batch(num_preload_transitions)
+            times = self.traj_time_sample_batch(traj_idxs)
+            self.preloaded_s = self.get_full_frame_at_time_batch(traj_idxs, times)
+            self.preloaded_s_next = self.get_full_frame_at_time_batch(traj_idxs, times + self.time_between_frames)
+
+    # ------------------------------------------------------------------ load time (host)
+    @classmethod
+    def _parse_motion_file(cls, path):
+        with open(path, "r") as f:
+            mj = json.load(f)
+        data = cls.reorder_from_pybullet_to_isaac(np.array(mj["Frames"], dtype=np.float64))
+        q = data[:, 3:7]
+        q = q / np.linalg.norm(q, axis=1, keepdims=True)        # pose3d.QuaternionNormalize
+        q = np.where(q[:, 3:4] < 0, -q, q)                      # motion_util.standardize_quaternion
+        data[:, 3:7] = q
+        return data, float(mj["FrameDuration"]), float(mj["MotionWeight"])
+
+    @staticmethod
+    def reorder_from_pybullet_to_isaac(motion_data):
+        """ML:134-164: legs [FR, FL, RR, RL] -> [FL, FR, RL, RR] in every 12-wide per-leg block."""
+        out = motion_data.copy()
+        for start in (7, 19, 37, 49):
+            blk = motion_data[:, start:start + 12].reshape(-1, 4, 3)
+            out[:, start:start + 12] = blk[:, [1, 0, 3, 2], :].reshape(-1, 12)
+        return out
+
+    # ------------------------------------------------------------------ sampling (host numpy RNG, ML:166-187)
+    def weighted_traj_idx_sample(self):
+        return np.random.choice(self.trajectory_idxs, p=self.trajectory_weights)
+
+    def weighted_traj_idx_sample_batch(self, size):
+        return np.random.choice(self.trajectory_idxs, size=size, p=self.trajectory_weights, replace=True)
+
+    def traj_time_sample(self, traj_idx):
+        subst = self.time_between_frames + self.trajectory_frame_durations[traj_idx]
+        return max(0, (self.trajectory_lens[traj_idx] * np.random.uniform() - subst))
+
+    def traj_time_sample_batch(self, traj_idxs):
+        subst = self.time_between_frames + self.trajectory_frame_durations[traj_idxs]
+        t = self.trajectory_lens[traj_idxs] * np.random.uniform(size=len(traj_idxs)) - subst
+        return np.maximum(np.zeros_like(t), t)
+
+    def slerp(self, val0, val1, blend):
+        return (1.0 - blend) * val0 + blend * val1
+
+    def get_trajectory(self, traj_idx):
+        return self.trajectories_full[traj_idx]
+
+    # ------------------------------------------------------------------ kernels
+    def get_full_frame_at_time_batch(self, traj_idxs, times, return_indices=False):
+        """ML:231-255 -> (B,49) fp32 on the device.  traj_idxs: int array, times: float64 array."""
+        idx_t = torch.as_tensor(np.asarray(traj_idxs, dtype=np.int64)).to(self.device, non_blocking=True)
+        times_t = torch.as_tensor(np.asarray(times, dtype=np.float64)).to(self.device, non_blocking=True)
+        return self.get_full_frame_at_time_batch_device(idx_t, times_t, return_indices)
+
+    def get_full_frame_at_time_batch_device(self, idx_t, times_t, return_indices=False):
+        b = idx_t.numel()
+        out = torch.empty(b, 49, device=self.device)
+        lo = hi = None
+        if return_indices:
+            lo = torch.empty(b, dtype=torch.int32, device=self.device)
+            hi = torch.empty(b, dtype=torch.int32, device=self.device)
+        L.check(L.lib.hl_amp_frame_blend(L.ptr(self.all_trajectories_full), L.ptr(self._clip_offset), L.ptr(self._clip_len),
+                                         L.ptr(self._clip_nf), len(self.trajectories_full), L.ptr(idx_t), L.ptr(times_t),
+                                         L.ptr(out), L.ptr(lo), L.ptr(hi), b, L.stream()))
+        return (out, lo, hi) if return_indices else out
+
+    def get_full_frame_batch(self, num_frames):
+        if self.preload_transitions:
+            idxs = np.random.choice(self.preloaded_s.shape[0], size=num_frames)
+            return self.preloaded_s[torch.as_tensor(idxs, device=self.device)]
+        traj_idxs = self.weighted_traj_idx_sample_batch(num_frames)
+        return self.get_full_frame_at_time_batch(traj_idxs, self.traj_time_sample_batch(traj_idxs))
+
+    def gather_pairs(self, idxs):
+        """(s, s_next) for preloaded rows `idxs` (host array or device tensor)."""
+        idx_t = idxs if isinstance(idxs, torch.Tensor) else torch.as_tensor(np.asarray(idxs, dtype=np.int64))
+        idx_t = idx_t.to(self.device, torch.long, non_blocking=True).contiguous()
+        b = idx_t.numel()
+        s = torch.empty(b, 30, device=self.device)
+        sn = torch.empty(b, 30, device=self.device)
+        L.check(L.lib.hl_amp_gather_pairs(L.ptr(self.preloaded_s), L.ptr(self.preloaded_s_next), self.preloaded_s.shape[0],
+                                          L.ptr(idx_t), L.ptr(s), L.ptr(sn), b, L.stream()))
+        return s, sn
+
+    def feed_forward_generator(self, num_mini_batch, mini_batch_size):
+        """ML:315-343: yields (s, s_next), each (mini_batch_size, 30)."""
+        for _ in range(num_mini_batch):
+            if self.preload_transitions:
+                idxs = np.random.choice(self.preloaded_s.shape[0], size=mini_batch_size)
+                yield self.gather_pairs(idxs)
+            else:
+                traj_idxs = self.weighted_traj_idx_sample_batch(mini_batch_size)
+                times = self.traj_time_sample_batch(traj_idxs)
+                pick = lambda fr: torch.cat([fr[:, 7:19], fr[:, 31:49]], dim=-1)
+                yield (pick(self.get_full_frame_at_time_batch(traj_idxs, times)),
+                       pick(self.get_full_frame_at_time_batch(traj_idxs, times + self.time_between_frames)))
+
+    @property
+    def observation_dim(self):
+        return self.trajectories[0].shape[1] - 12           # ML:346-349 -> 30
+
+    @property
+    def num_motions(self):
+        return len(self.trajectory_names)
+
+    # column accessors (ML:355-400)
+    @staticmethod
+    def get_root_pos_batch(p): return p[:, 0:3]
+    @staticmethod
+    def get_root_rot_batch(p): return p[:, 3:7]
+    @staticmethod
+    def get_joint_pose_batch(p): return p[:, 7:19]
+    @staticmethod
+    def get_tar_toe_pos_local_batch(p): return p[:, 19:31]
+    @staticmethod
+    def get_linear_vel_batch(p): return p[:, 31:34]
+    @staticmethod
+    def get_angular_vel_batch(p): return p[:, 34:37]
+    @staticmethod
+    def get_joint_vel_batch(p): return p[:, 37:49]

@@ -1,0 +1,106 @@
+"""CPU (-m "not gpu"): the C-ABI library loads and exports every symbol the header declares,
+struct layouts match, the host-side config logic follows the reference's rules, the mocap parser
+matches the reference loader, and the product path refuses to run without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    from isaacgymloco_b200 import _lib as L
+    header = open(os.path.join(ROOT, "include", "himloco_b200.h")).read()
+    declared = set(re.findall(r"\b(hl_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    raw = ctypes.CDLL(L.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in include/himloco_b200.h but not exported"
+    assert declared == set(L.EXPORTS), (declared ^ set(L.EXPORTS))
+    assert L.lib.hl_version() == 100
+    assert L.lib.hl_sizeof_cfg() == ctypes.sizeof(L.HlCfg)
+    assert L.lib.hl_sizeof_env_buffers() == ctypes.sizeof(L.HlEnvBuffers)
+
+
+def test_abi_guards_reject_bad_structs():
+    from isaacgymloco_b200 import _lib as L
+    from isaacgymloco_b200 import config as C
+    c = C.aliengo("flat").to_c()
+    c.struct_bytes = 12
+    b = L.HlEnvBuffers()
+    rc = L.lib.hl_post_physics_fused(ctypes.byref(c), ctypes.byref(b), 16, None)
+    assert rc == 1 and b"size mismatch" in L.lib.hl_last_error()
+    with pytest.raises(RuntimeError):
+        L.check(rc)
+    with pytest.raises(RuntimeError):
+        L.ptr(torch.zeros(4))            # CPU tensor: no fallback
+
+
+def test_no_cpu_fallback():
+    from isaacgymloco_b200.rollout_storage import HIMRolloutStorage
+    from isaacgymloco_b200.motion_loader import AMPLoader
+    from isaacgymloco_b200.legged_robot import FusedLeggedRobot
+    from isaacgymloco_b200 import config as C, synthetic as S
+    with pytest.raises(RuntimeError):
+        HIMRolloutStorage(8, 4, [270], [238], [12], device="cpu")
+    with pytest.raises(RuntimeError):
+        AMPLoader("cpu", 0.02, clip_tables=dict(frames=[np.zeros((3, 61))], frame_durations=[0.02], weights=[1]))
+    cfg = C.aliengo("flat", num_envs=8)
+    hf = S.make_terrain(cfg)
+    with pytest.raises(RuntimeError):
+        FusedLeggedRobot(cfg, S.make_state(cfg, 8, hf), hf, device="cpu")
+
+
+def test_reward_term_tables_follow_reference_rules():
+    from isaacgymloco_b200 import config as C
+    flat = C.aliengo("flat")
+    names, scales = flat.active_terms()
+    assert names == sorted(names) and len(names) == 21 and "termination" not in names
+    assert names[:3] == ["action_rate", "ang_vel_xy", "base_height"]
+    assert abs(scales[names.index("tracking_lin_vel")] - 1.5 * 0.02) < 1e-12
+    assert flat.termination_scale is None and flat.max_episode_length == 1000
+    st = C.aliengo("stairs", num_envs=16384)
+    n2, _ = st.active_terms()
+    assert len(n2) == 20 and abs(st.termination_scale + 50 * 0.02) < 1e-12
+    assert st.terrain_shape == (1300, 2300) and flat.terrain_shape == (1100, 1900)
+    sr = st.stumble_ranges()
+    assert (sr["stairsup_start"], sr["stairsup_end"], sr["pit_start"], sr["gap_end"]) == (3277, 8192, 16384, 16384)
+    assert st.episode_sum_names()[-1] == "termination"
+    nv = flat.noise_scale_vec()
+    assert nv.shape == (232,) and np.allclose(nv[3:6], 0.05) and np.allclose(nv[21:33], 0.075) and np.allclose(nv[45:], 0.5)
+    with pytest.raises(AttributeError):
+        C.aliengo("flat", reward_scales={"foot_clearance_base_terrain": -1.0}).active_terms()
+    with pytest.raises(NameError):
+        C.aliengo("flat", control_type="X").to_c()
+    c = st.to_c()
+    assert c.n_terms == 20 and c.has_termination_term == 1 and c.term_base_vel_violate == 1
+    assert [c.term_id[k] for k in range(3)] == [C.TERM_ID[n] for n in n2[:3]]
+    assert len(C.REWARD_TERMS) == 51 and C.REWARD_TERMS == sorted(C.REWARD_TERMS)
+
+
+def test_synthetic_state_is_deterministic_and_shaped():
+    from isaacgymloco_b200 import config as C, synthetic as S
+    cfg = C.aliengo("stairs", num_envs=64)
+    hf = S.make_terrain(cfg, seed=2)
+    assert hf.dtype == torch.int16 and tuple(hf.shape) == (1300, 2300) and int(hf.abs().max()) > 0
+    a, b = S.make_state(cfg, 64, hf, seed=3), S.make_state(cfg, 64, hf, seed=3)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert a["root_states"].shape == (64, 13) and a["dof_state"].shape == (768, 2)
+    assert a["rigid_body_states"].shape == (64 * 17, 13) and a["contact_forces"].shape == (64 * 17, 3)
+    assert a["episode_length_buf"].dtype == torch.long and a["last_contacts"].dtype == torch.bool
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/datasets/mocap_motions_aliengo"), reason="needs the reference's mocap clips (build container only)")
+def test_mocap_parser_matches_reference_loader():
+    from isaacgymloco_b200.motion_loader import AMPLoader
+    gold = load_golden("amp.npz")
+    d = "/root/reference/datasets/mocap_motions_aliengo"
+    for i, name in enumerate(gold["clip_names"]):
+        data, dur, w = AMPLoader._parse_motion_file(os.path.join(d, str(name)))
+        np.testing.assert_array_equal(data[:, :49].astype(np.float32), gold[f"clip{i}"])
+        assert dur == gold["frame_durations"][i] and w == gold["weights_raw"][i]

@@ -1,0 +1,195 @@
+"""-m gpu: GAE/returns and the AMP data path through the C ABI vs the reference fixtures and
+the torch oracle.  returns: bit-exact (same op order, no contraction); advantages: rel 1e-5;
+AMP frame indices / lerp columns / pair gathers / disc input: bit-exact; slerp columns rel 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _storage(n, t, r):
+    from isaacgymloco_b200.rollout_storage import HIMRolloutStorage
+    st = HIMRolloutStorage(n, t, [270], [238], [12], device="cuda:0")
+    st.rewards.copy_(r["rewards"])
+    st.values.copy_(r["values"])
+    st.dones.copy_(r["dones"])
+    return st
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c", "alldone"])
+def test_gae_vs_reference_golden(name):
+    from isaacgymloco_b200 import synthetic as S
+    gold = load_golden("gae.npz")
+    n, t, seed, gamma, lam = gold[f"{name}_meta"]
+    n, t = int(n), int(t)
+    r = S.make_rollout(n, t, int(seed))
+    if name == "alldone":
+        r["dones"][:] = 1
+    st = _storage(n, t, r)
+    st.compute_returns(r["last_values"].cuda(), gamma, lam)
+    assert st.returns.shape == (t, n, 1) and st.advantages.shape == (t, n, 1)
+    np.testing.assert_array_equal(st.returns.cpu().numpy(), gold[f"{name}_returns"])
+    np.testing.assert_allclose(st.advantages.cpu().numpy(), gold[f"{name}_advantages"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("n,t", [(4096, 24), (4096, 100), (65536, 24)])
+def test_gae_vs_oracle_full_size(n, t):
+    """configs[0]/[1] (4096 x 24), the real rollout length (T=100) and the 65,536-env shard."""
+    from isaacgymloco_b200 import synthetic as S
+    from oracle import torch_oracle as O
+    r = S.make_rollout(n, t, 7)
+    ret, adv = O.compute_returns(r["rewards"], r["values"], r["dones"], r["last_values"], 0.99, 0.95)
+    st = _storage(n, t, r)
+    st.compute_returns(r["last_values"].cuda(), 0.99, 0.95)
+    assert torch.equal(st.returns.cpu(), ret)
+    np.testing.assert_allclose(st.advantages.cpu().numpy(), adv.numpy(), rtol=1e-5, atol=2e-6)
+    # size-independent properties: normalised advantages have mean 0 / unbiased std 1, and
+    # returns - values recovers the un-normalised advantage up to that affine map
+    a = st.advantages.double()
+    assert abs(float(a.mean())) < 1e-5 and abs(float(a.std()) - 1.0) < 1e-5
+    raw = (st.returns - st.values).double()
+    np.testing.assert_allclose(((raw - raw.mean()) / (raw.std() + 1e-8)).cpu().numpy(), a.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_gae_linearity_and_terminal_cut():
+    """Domain properties: with dones=0, GAE is linear in (rewards, values); a done at step t makes
+    returns[<=t] independent of everything after t."""
+    from isaacgymloco_b200 import synthetic as S
+    n, t = 1024, 16
+    r = S.make_rollout(n, t, 11)
+    r["dones"][:] = 0
+    st = _storage(n, t, r)
+    st.compute_returns(r["last_values"].cuda(), 0.99, 0.95)
+    base = st.returns.clone()
+    r2 = {k: (v * 2 if v.dtype.is_floating_point else v) for k, v in r.items()}
+    st2 = _storage(n, t, r2)
+    st2.compute_returns(r2["last_values"].cuda(), 0.99, 0.95)
+    np.testing.assert_allclose(st2.returns.cpu().numpy(), 2 * base.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    r3 = {k: v.clone() for k, v in r.items()}
+    r3["dones"][7] = 1
+    st3 = _storage(n, t, r3)
+    st3.compute_returns(r3["last_values"].cuda(), 0.99, 0.95)
+    r4 = {k: v.clone() for k, v in r3.items()}
+    r4["rewards"][8:] += 5.0
+    r4["values"][8:] -= 3.0
+    r4["last_values"] += 1.0
+    st4 = _storage(n, t, r4)
+    st4.compute_returns(r4["last_values"].cuda(), 0.99, 0.95)
+    assert torch.equal(st3.returns[:8], st4.returns[:8])
+
+
+def _loader(gold, preload=False, n_pre=0):
+    from isaacgymloco_b200.motion_loader import AMPLoader
+    k = len(gold["frame_durations"])
+    tables = dict(frames=[gold[f"clip{i}"] for i in range(k)], frame_durations=gold["frame_durations"],
+                  weights=gold["weights_raw"], names=[str(x) for x in gold["clip_names"]])
+    return AMPLoader("cuda:0", 0.02, preload_transitions=preload, num_preload_transitions=n_pre, clip_tables=tables)
+
+
+def test_amp_frame_blend_vs_reference_golden():
+    gold = load_golden("amp.npz")
+    ld = _loader(gold)
+    assert ld.observation_dim == 30 and ld.num_motions == 7
+    np.testing.assert_array_equal(ld.trajectory_lens, gold["lens"])
+    np.testing.assert_array_equal(ld.trajectory_weights, gold["weights"])
+    out, lo, hi = ld.get_full_frame_at_time_batch(gold["blend_idx"], gold["blend_times"], return_indices=True)
+    p = gold["blend_times"] / gold["lens"][gold["blend_idx"]]
+    pn = p * gold["num_frames"][gold["blend_idx"]]
+    np.testing.assert_array_equal(lo.cpu().numpy(), np.floor(pn).astype(np.int32))
+    np.testing.assert_array_equal(hi.cpu().numpy(), np.ceil(pn).astype(np.int32))
+    got, want = out.cpu().numpy(), gold["blend_frames"]
+    lerp_cols = [c for c in range(49) if not 3 <= c < 7]
+    np.testing.assert_array_equal(got[:, lerp_cols], want[:, lerp_cols])
+    np.testing.assert_allclose(got[:, 3:7], want[:, 3:7], rtol=1e-5, atol=1e-6, equal_nan=True)
+
+
+def test_amp_frame_blend_config4_size():
+    """configs[3]: 16,384 samples per batch (and a 2e5-sample preload) vs the oracle."""
+    from oracle import torch_oracle as O
+    gold = load_golden("amp.npz")
+    ld = _loader(gold)
+    tab = O.OracleMotionTable([torch.from_numpy(gold[f"clip{i}"]) for i in range(7)], gold["frame_durations"],
+                              gold["weights_raw"], 0.02)
+    np.random.seed(5)
+    for b in (16384, 200000):
+        idx = ld.weighted_traj_idx_sample_batch(b)
+        times = ld.traj_time_sample_batch(idx)
+        want, lo, hi = tab.get_full_frame_at_time_batch(idx, times)
+        got, glo, ghi = ld.get_full_frame_at_time_batch(idx, times, return_indices=True)
+        np.testing.assert_array_equal(glo.cpu().numpy(), lo.astype(np.int32))
+        np.testing.assert_array_equal(ghi.cpu().numpy(), hi.astype(np.int32))
+        lerp_cols = [c for c in range(49) if not 3 <= c < 7]
+        np.testing.assert_array_equal(got.cpu().numpy()[:, lerp_cols], want.numpy()[:, lerp_cols])
+        np.testing.assert_allclose(got.cpu().numpy()[:, 3:7], want.numpy()[:, 3:7], rtol=1e-5, atol=1e-6, equal_nan=True)
+
+
+def test_amp_pairs_and_disc_reward_vs_reference_golden():
+    from isaacgymloco_b200.amp_discriminator import AMPDiscriminator, Normalizer
+    gold = load_golden("amp.npz")
+    ld = _loader(gold)
+    ld.preload_transitions = True
+    ld.preloaded_s = torch.from_numpy(gold["pre_s"]).cuda()
+    ld.preloaded_s_next = torch.from_numpy(gold["pre_s_next"]).cuda()
+    for k in (0, 1):
+        s, sn = ld.gather_pairs(gold[f"pair_idx{k}"])
+        np.testing.assert_array_equal(s.cpu().numpy(), gold[f"pair_s{k}"])
+        np.testing.assert_array_equal(sn.cpu().numpy(), gold[f"pair_sn{k}"])
+    # the generator consumes np.random exactly like the reference's (same idx stream)
+    np.random.seed(33)
+    pairs = list(ld.feed_forward_generator(2, 512))
+    np.testing.assert_array_equal(pairs[0][0].cpu().numpy(), gold["pair_s0"])
+    np.testing.assert_array_equal(pairs[1][1].cpu().numpy(), gold["pair_sn1"])
+    # normaliser: float64 device moments vs the reference's numpy update on fp32 batches
+    # (the reference accumulates np.mean/np.var in fp32 => agreement to ~1e-6 rel, not bit-exact)
+    norm = Normalizer(30)
+    norm.update(pairs[0][0])
+    norm.update(pairs[1][0])
+    np.testing.assert_allclose(norm.mean.cpu().numpy(), gold["norm_mean"], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(norm.var.cpu().numpy(), gold["norm_var"], rtol=2e-5, atol=1e-6)
+    assert abs(norm.count - float(gold["norm_count"])) < 1e-9
+    # discriminator reward with the golden normaliser state
+    norm.mean = torch.from_numpy(gold["norm_mean"]).cuda()
+    norm.var = torch.from_numpy(gold["norm_var"]).cuda()
+    torch.manual_seed(34)
+    disc = AMPDiscriminator(60, 0.01, [64, 32], "cuda:0", task_reward_lerp=0.3)
+    sd = {k: torch.from_numpy(gold["disc_" + k.replace(".", "_")]) for k in disc.state_dict()}
+    disc.load_state_dict(sd)
+    s, sn = torch.from_numpy(gold["disc_s"]).cuda(), torch.from_numpy(gold["disc_sn"]).cuda()
+    x = disc.assemble_input(s, sn, norm)
+    np.testing.assert_array_equal(x.cpu().numpy(), gold["disc_x"])
+    r, d = disc.predict_amp_reward(s, sn, torch.from_numpy(gold["disc_task_r"]).cuda(), normalizer=norm)
+    assert r.shape == (256,) and d.shape == (256, 1)
+    np.testing.assert_allclose(d.cpu().numpy(), gold["disc_d"], rtol=1e-4, atol=1e-5)   # cuBLAS vs CPU GEMM
+    # epilogue alone, on the golden logits: exact op order => bit-exact
+    from isaacgymloco_b200 import _lib as L
+    rr = torch.empty(256, device="cuda")
+    dd = torch.from_numpy(gold["disc_d"]).cuda().contiguous()
+    tr = torch.from_numpy(gold["disc_task_r"]).cuda()
+    L.check(L.lib.hl_amp_reward(L.ptr(dd), L.ptr(tr), 0.01, 0.3, L.ptr(rr), 256, L.stream()))
+    np.testing.assert_array_equal(rr.cpu().numpy(), gold["disc_r"])
+
+
+def test_amp_terminal_patch_config4():
+    """configs[3]: discriminator-input batch for 16,384 envs with the runner's terminal patch."""
+    from isaacgymloco_b200.amp_discriminator import AMPDiscriminator, Normalizer
+    from oracle import torch_oracle as O
+    n = 16384
+    g = torch.Generator().manual_seed(9)
+    s, sn = torch.randn(n, 30, generator=g), torch.randn(n, 30, generator=g)
+    ids = (torch.rand(n, generator=g) < 0.01).nonzero().flatten()
+    term = torch.randn(len(ids), 30, generator=g)
+    mean, var = np.random.default_rng(1).normal(size=30), np.random.default_rng(2).uniform(0.5, 2, size=30)
+    want_next = sn.clone()
+    want_next[ids] = term
+    want = O.amp_disc_input(s, want_next, mean, var)
+    norm = Normalizer(30)
+    norm.mean, norm.var = torch.from_numpy(mean).cuda(), torch.from_numpy(var).cuda()
+    disc = AMPDiscriminator(60, 0.01, [1024, 512], "cuda:0", task_reward_lerp=0.3)
+    x, patched = disc.assemble_input(s.cuda(), sn.cuda(), norm, ids.cuda(), term.cuda(), return_patched=True)
+    np.testing.assert_array_equal(patched.cpu().numpy(), want_next.numpy())
+    np.testing.assert_array_equal(x.cpu().numpy(), want.numpy())
+    x0 = disc.assemble_input(s.cuda(), sn.cuda(), None)
+    np.testing.assert_array_equal(x0.cpu().numpy(), torch.cat([s, sn], -1).numpy())
