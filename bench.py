@@ -185,7 +185,7 @@ class Workload:
         L.check(L.lib.hl_select_reset_ids(L.ptr(env.reset_buf), env.num_envs, L.ptr(env._reset_ids), L.ptr(env._n_reset),
                                           L.ptr(env._select_ws), L.stream()))
         env._terminal_rows(env._reset_ids, env._n_reset)
-        env.fused_post_reset()
+        env.fused_post_reset(with_reset_zero=True)   # no torch reset_idx in the replay loop
         env.common_step_counter += 1
         self.launches += env.cfg.decimation + 4
 

@@ -59,6 +59,7 @@ extern "C" {
 #define HL_ST_OBS_CLIP 0x200u    /* clip +-clip_observations (end of step())    LR:167-171    */
 #define HL_ST_ROLL 0x400u        /* disturbance=0, last_* <- current            LR:235-241    */
 #define HL_ST_BASE_HEIGHT 0x800u /* base_height_out = _get_base_heights()       LR:1357-1398  */
+#define HL_ST_RESET_ZERO 0x1000u /* the RNG-free buffer resets of reset_idx     LR:323-329,350,361 */
 #define HL_ST_ALL_STEP (HL_ST_COUNTERS | HL_ST_FRAME | HL_ST_CONTACTS | HL_ST_HEADING | HL_ST_HEIGHTS | \
                         HL_ST_TERMINATION | HL_ST_REWARD | HL_ST_OBS | HL_ST_OBS_CLIP | HL_ST_ROLL)
 
@@ -203,9 +204,11 @@ int hl_terminal_rows(const HlCfg* cfg, const HlEnvBuffers* bufs, const int64_t* 
 
 /* After reset_idx mutated the reset envs: re-scan their heights (LR:332-333), rewrite slot 0 of
  * obs_buf and privileged_obs_buf from the post-reset state (stale base velocities, LR:232) and
- * redo the end-of-step roll for them (LR:235-241). */
+ * redo the end-of-step roll for them (LR:235-241).  with_reset_zero != 0 first applies the
+ * RNG-free part of reset_idx itself (last_* / feet_air_time / episode_sums / episode_length_buf
+ * = 0, LR:323-329,350,361) for callers whose reset_idx does not (synthetic replay, bench). */
 int hl_post_reset_fixup(const HlCfg* cfg, const HlEnvBuffers* bufs, const int64_t* env_ids,
-                        const int32_t* n_ids_dev, int64_t n_envs, void* stream);
+                        const int32_t* n_ids_dev, int32_t with_reset_zero, int64_t n_envs, void* stream);
 
 /* get_amp_observations() for all envs -- LR:406-416: (N,30) = dof_pos, base_lin_vel,
  * base_ang_vel, dof_vel. */

@@ -33,7 +33,7 @@ class HlEnvBuffers(ctypes.Structure):
 # stage bits (include/himloco_b200.h)
 ST_COUNTERS, ST_FRAME, ST_CONTACTS, ST_HEADING, ST_HEIGHTS = 0x001, 0x002, 0x004, 0x008, 0x010
 ST_TERMINATION, ST_REWARD, ST_OBS, ST_OBS_NOSHIFT, ST_OBS_CLIP = 0x020, 0x040, 0x080, 0x100, 0x200
-ST_ROLL, ST_BASE_HEIGHT = 0x400, 0x800
+ST_ROLL, ST_BASE_HEIGHT, ST_RESET_ZERO = 0x400, 0x800, 0x1000
 
 EXPORTS = {
     "hl_version": (c_int32, []),
@@ -47,7 +47,7 @@ EXPORTS = {
     "hl_select_workspace_bytes": (c_int64, [c_int64]),
     "hl_select_reset_ids": (c_int32, [_vp, c_int64, _vp, _vp, _vp, _vp]),
     "hl_terminal_rows": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), _vp, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
-    "hl_post_reset_fixup": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), _vp, _vp, c_int64, _vp]),
+    "hl_post_reset_fixup": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), _vp, _vp, c_int32, c_int64, _vp]),
     "hl_amp_observations": (c_int32, [_vp, _vp, _vp, _vp, c_int64, _vp]),
     "hl_gae_scan": (c_int32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, c_int32, c_int64, c_float, c_float, _vp]),
     "hl_adv_normalize": (c_int32, [_vp, _vp, c_int64, _vp]),

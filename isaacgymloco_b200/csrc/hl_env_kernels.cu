@@ -103,20 +103,16 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Noise for 32 consecutive height points per iteration out of one Philox pass per 4 iterations:
-// in pass a, lane l owns block (a*32 + l) = uniforms for points 128a + 4l .. 4l+3; iteration
-// it = 4a + c needs, for point 32 it + l, component (l & 3) of the block held by lane 8c + l/4.
+// Height-scan noise: one Philox block per lane per pass = the uniforms of THAT lane's points in
+// iterations 4*pass .. 4*pass+3 (point 32*it + lane takes component it&3 of block pass*32+lane).
 struct HeightNoise {
   uint4 blk;
   __device__ __forceinline__ void refill(const HlEnvBuffers& b, unsigned long long genv, int pass, int lane, unsigned stream) {
     blk = hl_noise_block(b.philox_seed, b.philox_offset, genv, (unsigned)(pass * 32 + lane), stream);
   }
-  __device__ __forceinline__ float get(int it, int lane) const {
-    const int src = ((it & 3) << 3) + (lane >> 2);
-    const unsigned x = __shfl_sync(0xffffffffu, blk.x, src), y = __shfl_sync(0xffffffffu, blk.y, src);
-    const unsigned z = __shfl_sync(0xffffffffu, blk.z, src), w = __shfl_sync(0xffffffffu, blk.w, src);
-    const int cpt = lane & 3;
-    return hl_u01(cpt == 0 ? x : (cpt == 1 ? y : (cpt == 2 ? z : w)));
+  __device__ __forceinline__ float get(int it, int /*lane*/) const {
+    const int cpt = it & 3;
+    return hl_u01(cpt == 0 ? blk.x : (cpt == 1 ? blk.y : (cpt == 2 ? blk.z : blk.w)));
   }
 };
 
@@ -239,7 +235,10 @@ __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, 
     v.root = b.root_states + e * 13;
     v.dof = b.dof_state + e * 24;
     v.cf = b.contact_forces + e * B * 3;
-    for (int f = 0; f < 4; ++f) v.foot[f] = b.rigid_body_states + (e * B + c.feet_idx[f]) * 13;
+    for (int f = 0; f < 4; ++f) {
+      v.fpos[f] = b.rigid_body_states + (e * B + c.feet_idx[f]) * 13;
+      v.fvel[f] = v.fpos[f] + 7;
+    }
     v.act = b.actions + e * 12;
     v.lact = b.last_actions + e * 12;
     v.llact = b.last_last_actions + e * 12;
@@ -247,6 +246,23 @@ __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, 
     v.ldv = b.last_dof_vel + e * 12;
     v.tq = b.torques + e * 12;
     v.ltq = b.last_torques + e * 12;
+    if (stages & HL_ST_RESET_ZERO) {  // LR:323-329,350,361
+      if (lane < 12) {
+        b.last_actions[e * 12 + lane] = 0.0f;
+        b.last_last_actions[e * 12 + lane] = 0.0f;
+        b.last_dof_pos[e * 12 + lane] = 0.0f;
+        b.last_dof_vel[e * 12 + lane] = 0.0f;
+        b.last_torques[e * 12 + lane] = 0.0f;
+      }
+      if (lane < 4) b.feet_air_time[e * 4 + lane] = 0.0f;
+      if (b.episode_sums)
+        for (int k = lane; k < c.n_terms + c.has_termination_term; k += 32) b.episode_sums[(long long)k * n + e] = 0.0f;
+      if (lane == 0) {
+        b.episode_length_buf[e] = 0;
+        b.reset_buf[e] = 1;
+      }
+      __syncwarp();
+    }
     EnvScalars s;
     s.gid = e + c.env_id_offset;
     s.feet_shift = 0;
@@ -295,8 +311,8 @@ __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, 
       }
       if (lane < 12) {
         const int f = lane / 3, k = lane % 3;
-        if (b.feet_pos) b.feet_pos[e * 12 + lane] = v.foot[f][k];
-        if (b.feet_vel) b.feet_vel[e * 12 + lane] = v.foot[f][7 + k];
+        if (b.feet_pos) b.feet_pos[e * 12 + lane] = v.fpos[f][k];
+        if (b.feet_vel) b.feet_vel[e * 12 + lane] = v.fvel[f][k];
       }
     }
     if ((stages & HL_ST_HEADING) && c.heading_command) {
@@ -430,10 +446,12 @@ extern "C" int hl_post_physics_stages(const HlCfg* cfg, const HlEnvBuffers* bufs
 }
 
 extern "C" int hl_post_reset_fixup(const HlCfg* cfg, const HlEnvBuffers* bufs, const int64_t* env_ids,
-                                   const int32_t* n_ids_dev, int64_t n, void* stream) {
+                                   const int32_t* n_ids_dev, int32_t with_reset_zero, int64_t n, void* stream) {
   HL_CHECK_ARG(env_ids && n_ids_dev, "needs the reset id list");
-  return launch_stage(cfg, bufs, HL_ST_HEIGHTS | HL_ST_OBS | HL_ST_OBS_NOSHIFT | HL_ST_OBS_CLIP | HL_ST_ROLL, env_ids,
-                      n_ids_dev, n, stream);
+  return launch_stage(cfg, bufs,
+                      HL_ST_HEIGHTS | HL_ST_OBS | HL_ST_OBS_NOSHIFT | HL_ST_OBS_CLIP | HL_ST_ROLL |
+                          (with_reset_zero ? HL_ST_RESET_ZERO : 0u),
+                      env_ids, n_ids_dev, n, stream);
 }
 
 // ============================================================================= terminal rows
@@ -604,186 +622,331 @@ extern "C" int hl_select_reset_ids(const uint8_t* reset_buf, int64_t n, int64_t*
 }
 
 // ============================================================================= the fused step
-// One CTA = EPB consecutive envs.
-//   phase 0  coalesced slab loads of every AoS record into shared memory (odd row strides);
-//   phase 1  height scans, one warp per env: 187-point grid -> measured_heights + the height part
-//            of privileged_obs (noise fused), 63-point base grid -> base height;
-//   phase 2  one lane per env: frame, contacts, heading, termination, rewards, one-step obs;
-//   phase 3  coalesced stores: obs history shift (register-staged, in-place safe), slot 0,
-//            privileged_obs[0:51], the last_* roll.
+// One CTA (8 warps) = EPB = 64 consecutive envs.
+//   phase 0  128-bit coalesced slab loads of every AoS record into shared memory (odd row strides
+//            => conflict-free one-lane-per-env reads); only pos/vel of the 4 foot records are
+//            fetched from rigid_body_states.
+//   phase 1  warp-specialised, concurrently:
+//              warps 0-1  one lane per env: frame, contacts, heading, termination, one-step obs
+//                         (+noise), then -- after the base heights arrive (named barrier) -- the
+//                         reward terms and episode sums;
+//              warps 2-7  height scans, one warp per env: 63-point base grid first (-> base
+//                         height), then the 187-point grid -> measured_heights + the height part
+//                         of privileged_obs (noise, scale, clip fused).  Each lane owns fixed grid
+//                         points (coordinates in registers); every op of the index path is
+//                         rounded on its own in the reference's order.
+//   phase 2  coalesced stores: obs history shift (register-staged, in-place safe), slot 0,
+//            privileged_obs[0:51], the last_* roll (skipped for envs that reset: the post-reset
+//            fix-up redoes it after reset_idx).
 constexpr int EPB = 64;
 constexpr int FUSED_THREADS = 256;
-constexpr int S13 = 13, SDOF = 25, SFOOT = 53, SCUR = 51;
+constexpr int SCALAR_WARPS = 2;
+constexpr int SCAN_WARPS = FUSED_THREADS / 32 - SCALAR_WARPS;
+constexpr int S13 = 13, SDOF = 25, SFOOT = 25, SCUR = 51;
+constexpr int ENVS_PER_SCAN_WARP = (EPB + SCAN_WARPS - 1) / SCAN_WARPS;
 
 struct FusedSmem {
   float root[EPB * S13];
   float dof[EPB * SDOF];
-  float foot[EPB * SFOOT];
-  float act[EPB * S13], lact[EPB * S13], llact[EPB * S13], ldp[EPB * S13], ldv[EPB * S13], tq[EPB * S13], ltq[EPB * S13];
+  float foot[EPB * SFOOT];   // per env: foot f -> pos3 at [6f], vel3 at [6f+3]
+  float act[EPB * S13], lact[EPB * S13], llact[EPB * S13], ldv[EPB * S13], tq[EPB * S13];
   float cur[EPB * SCUR];
   float base_h[EPB];
   unsigned char reset[EPB];
-  // contact forces follow (EPB * cf_stride floats), sized at launch
+  // dynamic tail: contact forces (EPB*cf_stride), then optional last_dof_pos / last_torques slabs
 };
 
-// global (count x rec contiguous) -> shared rows of `stride`
-__device__ __forceinline__ void stage_in(float* dst, int stride, const float* __restrict__ src, int rec, int count, int tid) {
-  const int total = count * rec;
-  int e = tid / rec, k = tid - e * rec;
-  const int de = FUSED_THREADS / rec, dk = FUSED_THREADS - de * rec;
-  for (int i = tid; i < total; i += FUSED_THREADS) {
-    dst[e * stride + k] = __ldg(src + i);
-    e += de;
-    k += dk;
-    if (k >= rec) { k -= rec; ++e; }
+// global (count x REC contiguous floats, 16-B aligned slab) -> shared rows of STRIDE, float4 loads
+template <int REC, int STRIDE>
+__device__ __forceinline__ void stage_in4(float* dst, const float* __restrict__ src, int count, int tid) {
+  const int total = count * REC;
+  const int n4 = total >> 2;
+  const float4* src4 = reinterpret_cast<const float4*>(src);
+  for (int i = tid; i < n4; i += FUSED_THREADS) {
+    const float4 v = __ldg(src4 + i);
+    const int base = i << 2;
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = base + j, e = idx / REC, k = idx - e * REC;
+      dst[e * STRIDE + k] = vv[j];
+    }
+  }
+  for (int idx = (n4 << 2) + tid; idx < total; idx += FUSED_THREADS) {
+    const int e = idx / REC, k = idx - e * REC;
+    dst[e * STRIDE + k] = __ldg(src + idx);
   }
 }
-// shared rows -> global (count x rec contiguous); rows whose env resets are left to the
-// post-reset fix-up (hl_post_reset_fixup), which redoes the roll after reset_idx ran
-__device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* src, int stride, int rec, int count, int tid,
-                                          const unsigned char* skip) {
+// runtime record size (contact forces)
+__device__ __forceinline__ void stage_in4_rt(float* dst, int stride, const float* __restrict__ src, int rec, int count, int tid) {
   const int total = count * rec;
-  int e = tid / rec, k = tid - e * rec;
-  const int de = FUSED_THREADS / rec, dk = FUSED_THREADS - de * rec;
-  for (int i = tid; i < total; i += FUSED_THREADS) {
-    if (!skip[e]) dst[i] = src[e * stride + k];
-    e += de;
-    k += dk;
-    if (k >= rec) { k -= rec; ++e; }
+  const int n4 = total >> 2;
+  const float4* src4 = reinterpret_cast<const float4*>(src);
+  for (int i = tid; i < n4; i += FUSED_THREADS) {
+    const float4 v = __ldg(src4 + i);
+    const int base = i << 2;
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    int e = base / rec, k = base - e * rec;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dst[e * stride + k] = vv[j];
+      if (++k == rec) { k = 0; ++e; }
+    }
+  }
+  for (int idx = (n4 << 2) + tid; idx < total; idx += FUSED_THREADS) {
+    const int e = idx / rec, k = idx - e * rec;
+    dst[e * stride + k] = __ldg(src + idx);
+  }
+}
+// shared rows -> global (count x 12 contiguous); rows whose env resets are left to the fix-up
+__device__ __forceinline__ void stage_out12(float* __restrict__ dst, const float* src, int count, int tid,
+                                            const unsigned char* skip) {
+  for (int i = tid; i < count * 12; i += FUSED_THREADS) {
+    const int e = i / 12, k = i - e * 12;
+    if (!skip[e]) dst[i] = src[e * S13 + k];
   }
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS) hl_post_physics_fused_kernel(HlCfg c, HlEnvBuffers b, long long n,
-                                                                              int cf_stride, int need_ldp, int need_ltq) {
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// cell index of one coordinate, fused path (int32 is enough: cvt saturates exactly where the
+// reference's clip would land; NaN -> 0 either way)
+template <bool CPU_MATH>
+__device__ __forceinline__ int cell32(float world, float border, float hs, float inv_hs, int hi) {
+  const float p = __fadd_rn(world, border);
+  const float g = CPU_MATH ? __fdiv_rn(p, hs) : __fmul_rn(p, inv_hs);
+  return min(max(__float2int_rz(g), 0), hi);
+}
+
+// raw min-of-3 height (int16 units) under body-frame point (bx,by): the reference's op order,
+// every product/sum rounded separately (see hl_scan_axis_* in hl_math.cuh)
+template <bool CPU_MATH>
+__device__ __forceinline__ int scan_gather(const HlCfg& c, const int16_t* __restrict__ min3, int pitch, float qz, float qw,
+                                           float posx, float posy, float bx, float by) {
+  const float ty = 2.0f * __fmul_rn(qz, bx), tx = -2.0f * __fmul_rn(qz, by);
+  const float ay = __fmul_rn(qw, ty), cx = -__fmul_rn(qz, ty);
+  const float ax = __fmul_rn(qw, tx), cy = __fmul_rn(qz, tx);
+  const float rx = __fadd_rn(__fadd_rn(bx, ax), cx);
+  const float ry = __fadd_rn(__fadd_rn(by, ay), cy);
+  const int ix = cell32<CPU_MATH>(__fadd_rn(rx, posx), c.border_size, c.horizontal_scale, c.inv_horizontal_scale, c.terrain_rows - 2);
+  const int iy = cell32<CPU_MATH>(__fadd_rn(ry, posy), c.border_size, c.horizontal_scale, c.inv_horizontal_scale, c.terrain_cols - 2);
+  return (int)__ldg(min3 + ix * pitch + iy);
+}
+
+template <bool CPU_MATH, int NIT, int NBIT>
+__global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel(HlCfg c, HlEnvBuffers b, long long n, int cf_stride,
+                                                                                 int need_ldp, int need_ltq, int want_base) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
   float* s_cf = reinterpret_cast<float*>(smem_raw + sizeof(FusedSmem));
+  float* s_ldp = s_cf + EPB * cf_stride;
+  float* s_ltq = s_ldp + (need_ldp ? EPB * S13 : 0);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const long long e0 = (long long)blockIdx.x * EPB;
   const int cnt = (int)((n - e0) < EPB ? (n - e0) : EPB);
-  const int B = c.num_bodies, P = c.n_px * c.n_py, PD = hl_priv_dim(c);
+  const int B = c.num_bodies, P = c.n_px * c.n_py, PD = 51 + P;
 
-  // ---------------- phase 0: stage inputs
-  stage_in(sm.root, S13, b.root_states + e0 * 13, 13, cnt, tid);
-  stage_in(sm.dof, SDOF, b.dof_state + e0 * 24, 24, cnt, tid);
-  stage_in(s_cf, cf_stride, b.contact_forces + e0 * B * 3, B * 3, cnt, tid);
-  for (int i = tid; i < cnt * 52; i += FUSED_THREADS) {
-    const int e = i / 52, r = i - e * 52, f = r / 13, k = r - f * 13;
-    sm.foot[e * SFOOT + r] = __ldg(b.rigid_body_states + ((e0 + e) * B + c.feet_idx[f]) * 13 + k);
+  // ---------------- phase 0: stage inputs (float4, coalesced)
+  stage_in4<13, S13>(sm.root, b.root_states + e0 * 13, cnt, tid);
+  stage_in4<24, SDOF>(sm.dof, b.dof_state + e0 * 24, cnt, tid);
+  stage_in4_rt(s_cf, cf_stride, b.contact_forces + e0 * B * 3, B * 3, cnt, tid);
+  for (int i = tid; i < cnt * 24; i += FUSED_THREADS) {  // pos/vel of the 4 foot records only
+    const int e = i / 24, r = i - e * 24, f = r / 6, k = r - f * 6;
+    sm.foot[e * SFOOT + r] = __ldg(b.rigid_body_states + ((e0 + e) * B + c.feet_idx[f]) * 13 + (k < 3 ? k : k + 4));
   }
-  stage_in(sm.act, S13, b.actions + e0 * 12, 12, cnt, tid);
-  stage_in(sm.lact, S13, b.last_actions + e0 * 12, 12, cnt, tid);
-  stage_in(sm.llact, S13, b.last_last_actions + e0 * 12, 12, cnt, tid);
-  stage_in(sm.ldv, S13, b.last_dof_vel + e0 * 12, 12, cnt, tid);
-  stage_in(sm.tq, S13, b.torques + e0 * 12, 12, cnt, tid);
-  if (need_ldp) stage_in(sm.ldp, S13, b.last_dof_pos + e0 * 12, 12, cnt, tid);
-  if (need_ltq) stage_in(sm.ltq, S13, b.last_torques + e0 * 12, 12, cnt, tid);
+  stage_in4<12, S13>(sm.act, b.actions + e0 * 12, cnt, tid);
+  stage_in4<12, S13>(sm.lact, b.last_actions + e0 * 12, cnt, tid);
+  stage_in4<12, S13>(sm.llact, b.last_last_actions + e0 * 12, cnt, tid);
+  stage_in4<12, S13>(sm.ldv, b.last_dof_vel + e0 * 12, cnt, tid);
+  stage_in4<12, S13>(sm.tq, b.torques + e0 * 12, cnt, tid);
+  if (need_ldp) stage_in4<12, S13>(s_ldp, b.last_dof_pos + e0 * 12, cnt, tid);
+  if (need_ltq) stage_in4<12, S13>(s_ltq, b.last_torques + e0 * 12, cnt, tid);
   __syncthreads();
 
-  // ---------------- phase 1: height scans (warp per env)
-  const bool want_base = hl_needs_base_height(c);
-  for (int e = wid; e < cnt; e += FUSED_THREADS / 32) {
-    const long long ge = e0 + e;
-    ScanOut o;
-    o.measured = b.measured_heights + ge * P;
-    o.priv_heights = b.privileged_obs_buf + ge * PD + 51;
-    o.idx = nullptr;
-    o.u187 = b.noise_u187 ? b.noise_u187 + ge * P : nullptr;
-    o.clip = true;
-    o.keep = nullptr;
-    const float bh = hl_warp_scan_env(c, b, sm.root + e * S13, (unsigned long long)(ge + c.env_id_offset), lane,
-                                      c.measure_heights != 0, want_base, o, 0u);
-    if (lane == 0) sm.base_h[e] = bh;
-  }
-  __syncthreads();
-
-  // ---------------- phase 2: one lane per env
-  if (tid < cnt) {
+  if (wid < SCALAR_WARPS) {
+    // ---------------- phase 1a: one lane per env
     const int e = tid;
-    const long long ge = e0 + e;
+    const bool act_lane = e < cnt;
+    const long long ge = e0 + (act_lane ? e : 0);
     EnvView v;
-    v.root = sm.root + e * S13;
-    v.dof = sm.dof + e * SDOF;
-    v.cf = s_cf + e * cf_stride;
-    for (int f = 0; f < 4; ++f) v.foot[f] = sm.foot + e * SFOOT + f * 13;
-    v.act = sm.act + e * S13;
-    v.lact = sm.lact + e * S13;
-    v.llact = sm.llact + e * S13;
-    v.ldp = sm.ldp + e * S13;
-    v.ldv = sm.ldv + e * S13;
-    v.tq = sm.tq + e * S13;
-    v.ltq = sm.ltq + e * S13;
     EnvScalars s;
-    s.gid = ge + c.env_id_offset;
-    s.feet_shift = 0;
-    s.base_h = sm.base_h[e];
-    s.terrain_level = b.terrain_levels ? b.terrain_levels[ge] : 0;
-    s.ep_len = b.episode_length_buf[ge] + 1;  // LR:193
-    const float4 cm = reinterpret_cast<const float4*>(b.commands)[ge];
-    s.cmd[0] = cm.x; s.cmd[1] = cm.y; s.cmd[2] = cm.z; s.cmd[3] = cm.w;
-    const float4 ar = reinterpret_cast<const float4*>(b.feet_air_time)[ge];
-    s.air[0] = ar.x; s.air[1] = ar.y; s.air[2] = ar.z; s.air[3] = ar.w;
-    const unsigned lc4 = reinterpret_cast<const unsigned*>(b.last_contacts)[ge];
-    unsigned last = 0;
+    if (act_lane) {
+      v.root = sm.root + e * S13;
+      v.dof = sm.dof + e * SDOF;
+      v.cf = s_cf + e * cf_stride;
+      for (int f = 0; f < 4; ++f) {
+        v.fpos[f] = sm.foot + e * SFOOT + f * 6;
+        v.fvel[f] = v.fpos[f] + 3;
+      }
+      v.act = sm.act + e * S13;
+      v.lact = sm.lact + e * S13;
+      v.llact = sm.llact + e * S13;
+      v.ldp = s_ldp + e * S13;
+      v.ldv = sm.ldv + e * S13;
+      v.tq = sm.tq + e * S13;
+      v.ltq = s_ltq + e * S13;
+      s.gid = ge + c.env_id_offset;
+      s.feet_shift = 0;
+      s.base_h = 0.0f;
+      s.terrain_level = b.terrain_levels ? b.terrain_levels[ge] : 0;
+      s.ep_len = b.episode_length_buf[ge] + 1;  // LR:193
+      const float4 cm = reinterpret_cast<const float4*>(b.commands)[ge];
+      s.cmd[0] = cm.x; s.cmd[1] = cm.y; s.cmd[2] = cm.z; s.cmd[3] = cm.w;
+      const float4 ar = reinterpret_cast<const float4*>(b.feet_air_time)[ge];
+      s.air[0] = ar.x; s.air[1] = ar.y; s.air[2] = ar.z; s.air[3] = ar.w;
+      const unsigned lc4 = reinterpret_cast<const unsigned*>(b.last_contacts)[ge];
+      unsigned last = 0;
 #pragma unroll
-    for (int f = 0; f < 4; ++f) last |= (((lc4 >> (8 * f)) & 0xffu) ? 1u : 0u) << f;
-    hl_frame(v, s);
-    hl_contacts(c, v, last, s);
-    if (c.heading_command) s.cmd[2] = hl_heading_command(v.root + 3, s.cmd[3]);
-    hl_check_termination(c, v, s);
-    const float rew = hl_compute_reward(c, b, v, s, b.episode_sums ? b.episode_sums + ge : nullptr, n, true);
-
-    b.episode_length_buf[ge] = s.ep_len;
-    b.commands[ge * 4 + 2] = s.cmd[2];
-    b.reset_buf[ge] = s.reset;
-    b.time_out_buf[ge] = s.time_out;
-    b.rew_buf[ge] = rew;
-    sm.reset[e] = s.reset;
-    unsigned cf4 = 0, lc = 0;
+      for (int f = 0; f < 4; ++f) last |= (((lc4 >> (8 * f)) & 0xffu) ? 1u : 0u) << f;
+      hl_frame(v, s);
+      hl_contacts(c, v, last, s);
+      if (c.heading_command) s.cmd[2] = hl_heading_command(v.root + 3, s.cmd[3]);
+      hl_check_termination(c, v, s);
+      b.episode_length_buf[ge] = s.ep_len;
+      b.commands[ge * 4 + 2] = s.cmd[2];
+      b.reset_buf[ge] = s.reset;
+      b.time_out_buf[ge] = s.time_out;
+      sm.reset[e] = s.reset;
+      unsigned cf4 = 0;
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      cf4 |= ((s.cfilt >> f) & 1u) << (8 * f);
-      lc |= ((s.last_contact >> f) & 1u) << (8 * f);
-    }
-    reinterpret_cast<unsigned*>(b.contact_filt)[ge] = cf4;
-    reinterpret_cast<unsigned*>(b.last_contacts)[ge] = lc;
-    reinterpret_cast<float4*>(b.feet_air_time)[ge] = make_float4(s.air[0], s.air[1], s.air[2], s.air[3]);
+      for (int f = 0; f < 4; ++f) cf4 |= ((s.cfilt >> f) & 1u) << (8 * f);
+      reinterpret_cast<unsigned*>(b.contact_filt)[ge] = cf4;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      b.base_lin_vel[ge * 3 + k] = s.blv[k];
-      b.base_ang_vel[ge * 3 + k] = s.bav[k];
-      b.projected_gravity[ge * 3 + k] = s.pg[k];
-    }
-    // one-step observation (+noise), clipped: LR:385-394,167-171
-    float* cur = sm.cur + e * SCUR;
-    const float cl = c.clip_obs;
-    if (c.add_noise && !b.noise_u45) {
-      for (int kb = 0; kb < 12; ++kb) {
-        const uint4 r = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)s.gid, (unsigned)kb, 2u);
-        const unsigned rr[4] = {r.x, r.y, r.z, r.w};
+      for (int k = 0; k < 3; ++k) {
+        b.base_lin_vel[ge * 3 + k] = s.blv[k];
+        b.base_ang_vel[ge * 3 + k] = s.bav[k];
+        b.projected_gravity[ge * 3 + k] = s.pg[k];
+      }
+      // one-step observation (+noise), clipped: LR:385-394,167-171
+      float* cur = sm.cur + e * SCUR;
+      const float cl = c.clip_obs;
+      if (c.add_noise && !b.noise_u45) {
+#pragma unroll 1
+        for (int kb = 0; kb < 12; ++kb) {
+          const uint4 r = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)s.gid, (unsigned)kb, 2u);
+          const unsigned rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = kb * 4 + j;
-          if (k < 45) cur[k] = hl_clampf(hl_add_noise45(c, hl_obs45(c, v, s, k), hl_u01(rr[j]), k), -cl, cl);
+          for (int j = 0; j < 4; ++j) {
+            const int k = kb * 4 + j;
+            if (k < 45) cur[k] = hl_clampf(hl_add_noise45(c, hl_obs45(c, v, s, k), hl_u01(rr[j]), k), -cl, cl);
+          }
+        }
+      } else {
+        for (int k = 0; k < 45; ++k) {
+          const float u = (c.add_noise && b.noise_u45) ? b.noise_u45[ge * 45 + k] : 0.5f;
+          cur[k] = hl_clampf(hl_add_noise45(c, hl_obs45(c, v, s, k), u, k), -cl, cl);
         }
       }
-    } else {
-      for (int k = 0; k < 45; ++k) {
-        const float u = (c.add_noise && b.noise_u45) ? b.noise_u45[ge * 45 + k] : 0.5f;
-        cur[k] = hl_clampf(hl_add_noise45(c, hl_obs45(c, v, s, k), u, k), -cl, cl);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        cur[45 + k] = hl_clampf(s.blv[k] * c.obs_lin_vel, -cl, cl);
+        float* dptr = b.disturbance + ge * B * 3 + k;
+        cur[48 + k] = hl_clampf(*dptr, -cl, cl);
+        if (!s.reset) *dptr = 0.0f;  // LR:235; reset envs: the fix-up still reads it, then zeroes it
       }
     }
+    if (want_base) named_bar_sync(1, FUSED_THREADS);  // base heights are in shared memory
+    if (act_lane) {
+      s.base_h = sm.base_h[e];
+      const float rew = hl_compute_reward(c, b, v, s, b.episode_sums ? b.episode_sums + ge : nullptr, n, true);
+      b.rew_buf[ge] = rew;
+      unsigned lc = 0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      cur[45 + k] = hl_clampf(s.blv[k] * c.obs_lin_vel, -cl, cl);
-      float* dptr = b.disturbance + ge * B * 3 + k;
-      cur[48 + k] = hl_clampf(*dptr, -cl, cl);
-      if (!s.reset) *dptr = 0.0f;  // LR:235; reset envs are zeroed by the post-reset fix-up, which still reads it
+      for (int f = 0; f < 4; ++f) lc |= ((s.last_contact >> f) & 1u) << (8 * f);
+      reinterpret_cast<unsigned*>(b.last_contacts)[ge] = lc;
+      reinterpret_cast<float4*>(b.feet_air_time)[ge] = make_float4(s.air[0], s.air[1], s.air[2], s.air[3]);
+    }
+  } else {
+    // ---------------- phase 1b: height scans, one warp per env
+    const int sw = wid - SCALAR_WARPS;
+    const int16_t* __restrict__ min3 = b.height_min3;
+    const int pitch = c.terrain_cols - 1;
+    const bool plane = c.mesh_type == 0;
+    // this lane's grid points (body frame), fixed for the whole kernel
+    float gx[NIT], gy[NIT], hx[NBIT], hy[NBIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int p = min(it * 32 + lane, P - 1), i = p / c.n_py, j = p - i * c.n_py;
+      gx[it] = c.px[i];
+      gy[it] = c.py[j];
+    }
+    const int PB = c.n_bx * c.n_by;
+#pragma unroll
+    for (int it = 0; it < NBIT; ++it) {
+      const int p = min(it * 32 + lane, PB - 1), i = p / c.n_by, j = p - i * c.n_by;
+      hx[it] = c.bx[i];
+      hy[it] = c.by[j];
+    }
+    // yaw quaternions of this warp's envs: lane l normalises env sw + SCAN_WARPS*l, broadcast later
+    float qz_l = 0.0f, qw_l = 1.0f;
+    {
+      const int e = sw + SCAN_WARPS * lane;
+      if (lane < ENVS_PER_SCAN_WARP && e < cnt) hl_yaw_quat(sm.root + e * S13 + 3, qz_l, qw_l);
+    }
+    if (want_base) {
+      for (int li = 0, e = sw; e < cnt; e += SCAN_WARPS, ++li) {
+        const float qz = __shfl_sync(0xffffffffu, qz_l, li), qw = __shfl_sync(0xffffffffu, qw_l, li);
+        const float* root = sm.root + e * S13;
+        const float posx = root[0], posy = root[1], posz = root[2];
+        float acc = 0.0f;
+        if (plane) {
+          acc = lane == 0 ? posz * (float)PB : 0.0f;
+        } else {
+          int hraw[NBIT];
+#pragma unroll
+          for (int it = 0; it < NBIT; ++it) hraw[it] = scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, posx, posy, hx[it], hy[it]);
+#pragma unroll
+          for (int it = 0; it < NBIT; ++it)
+            if (it * 32 + lane < PB) acc += posz - (float)hraw[it] * c.vertical_scale;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) sm.base_h[e] = plane ? posz : acc / (float)PB;
+      }
+      __threadfence_block();
+      named_bar_arrive(1, FUSED_THREADS);
+    }
+    const bool philox = c.add_noise && !b.noise_u187;
+    const float cl = c.clip_obs;
+    for (int li = 0, e = sw; e < cnt; e += SCAN_WARPS, ++li) {
+      const long long ge = e0 + e;
+      const float qz = __shfl_sync(0xffffffffu, qz_l, li), qw = __shfl_sync(0xffffffffu, qw_l, li);
+      const float* root = sm.root + e * S13;
+      const float posx = root[0], posy = root[1], posz = root[2];
+      int hraw[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it)
+        hraw[it] = plane ? 0 : scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, posx, posy, gx[it], gy[it]);
+      uint4 nz[(NIT + 3) / 4];
+      if (philox) {
+#pragma unroll
+        for (int a = 0; a < (NIT + 3) / 4; ++a)
+          nz[a] = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)(ge + c.env_id_offset), (unsigned)(a * 32 + lane), 0u);
+      }
+      float* mrow = b.measured_heights + ge * P;
+      float* prow = b.privileged_obs_buf + ge * PD + 51;
+      const float* urow = b.noise_u187 ? b.noise_u187 + ge * P : nullptr;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int p = it * 32 + lane;
+        if (p < P) {
+          const float mh = (float)hraw[it] * c.vertical_scale;
+          float u = 0.5f;
+          if (philox) {
+            const uint4 q = nz[it >> 2];
+            u = hl_u01((it & 3) == 0 ? q.x : ((it & 3) == 1 ? q.y : ((it & 3) == 2 ? q.z : q.w)));
+          } else if (urow) {
+            u = urow[p];
+          }
+          mrow[p] = mh;
+          prow[p] = hl_clampf(hl_obs_height(c, posz, mh, u), -cl, cl);
+        }
+      }
     }
   }
   __syncthreads();
 
-  // ---------------- phase 3: stores
+  // ---------------- phase 2: stores
   for (int e = wid; e < cnt; e += FUSED_THREADS / 32) {
     const long long ge = e0 + e;
     const float* src = b.obs_buf_in + ge * 270;
@@ -809,9 +972,9 @@ __global__ void __launch_bounds__(FUSED_THREADS) hl_post_physics_fused_kernel(Hl
     }
   }
   // end-of-step roll (LR:235-241) for the envs that do not reset
-  stage_out(b.last_last_actions + e0 * 12, sm.lact, S13, 12, cnt, tid, sm.reset);
-  stage_out(b.last_actions + e0 * 12, sm.act, S13, 12, cnt, tid, sm.reset);
-  stage_out(b.last_torques + e0 * 12, sm.tq, S13, 12, cnt, tid, sm.reset);
+  stage_out12(b.last_last_actions + e0 * 12, sm.lact, cnt, tid, sm.reset);
+  stage_out12(b.last_actions + e0 * 12, sm.act, cnt, tid, sm.reset);
+  stage_out12(b.last_torques + e0 * 12, sm.tq, cnt, tid, sm.reset);
   for (int i = tid; i < cnt * 12; i += FUSED_THREADS) {
     const int e = i / 12, d = i - e * 12;
     if (sm.reset[e]) continue;
@@ -826,10 +989,28 @@ __global__ void __launch_bounds__(FUSED_THREADS) hl_post_physics_fused_kernel(Hl
   if (b.feet_pos || b.feet_vel) {
     for (int i = tid; i < cnt * 12; i += FUSED_THREADS) {
       const int e = i / 12, r = i - e * 12, f = r / 3, k = r - f * 3;
-      if (b.feet_pos) b.feet_pos[e0 * 12 + i] = sm.foot[e * SFOOT + f * 13 + k];
-      if (b.feet_vel) b.feet_vel[e0 * 12 + i] = sm.foot[e * SFOOT + f * 13 + 7 + k];
+      if (b.feet_pos) b.feet_pos[e0 * 12 + i] = sm.foot[e * SFOOT + f * 6 + k];
+      if (b.feet_vel) b.feet_vel[e0 * 12 + i] = sm.foot[e * SFOOT + f * 6 + 3 + k];
     }
   }
+}
+
+template <bool CPU_MATH, int NIT, int NBIT>
+static int launch_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, int cf_stride, int need_ldp, int need_ltq,
+                        int want_base, size_t smem, cudaStream_t stream) {
+  auto kern = hl_post_physics_fused_kernel<CPU_MATH, NIT, NBIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      hl_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return HL_E_CUDA;
+    }
+    attr_set = true;
+  }
+  const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
+  kern<<<blocks, FUSED_THREADS, smem, stream>>>(*cfg, *bufs, n, cf_stride, need_ldp, need_ltq, want_base);
+  return HL_OK;
 }
 
 extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, void* stream) {
@@ -842,29 +1023,31 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
                    b.measured_heights && b.reset_buf && b.time_out_buf && b.rew_buf && b.obs_buf_in && b.obs_buf_out &&
                    b.privileged_obs_buf,
                "null buffer");
-  HL_CHECK_ARG(cfg->mesh_type == 0 || b.height_samples || b.height_min3, "terrain table missing");
+  HL_CHECK_ARG(cfg->mesh_type == 0 || b.height_min3, "the fused step needs the min3 terrain table (hl_terrain_prepare)");
   HL_CHECK_ARG(cfg->measure_heights, "the fused step needs measure_heights (privileged obs carries the scan)");
   if (n <= 0) return HL_OK;
   int cf_stride = cfg->num_bodies * 3;
   if ((cf_stride & 1) == 0) cf_stride += 1;
-  int need_ldp = 0, need_ltq = 0;
+  int need_ldp = 0, need_ltq = 0, want_base = 0;
   for (int k = 0; k < cfg->n_terms; ++k) {
     need_ldp |= cfg->term_id[k] == T_dof_pos_dif;
     need_ltq |= cfg->term_id[k] == T_torques_dif;
+    want_base |= cfg->term_id[k] == T_base_height || cfg->term_id[k] == T_base_height_up;
   }
-  const size_t smem = sizeof(FusedSmem) + (size_t)EPB * cf_stride * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(hl_post_physics_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) {
-      hl_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return HL_E_CUDA;
-    }
-    attr_set = true;
-  }
+  const size_t smem = sizeof(FusedSmem) + (size_t)EPB * (cf_stride + (need_ldp ? S13 : 0) + (need_ltq ? S13 : 0)) * sizeof(float);
   HL_CHECK_ARG(smem <= 200 * 1024, "num_bodies too large for the shared-memory slab");
-  const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
-  hl_post_physics_fused_kernel<<<blocks, FUSED_THREADS, smem, (cudaStream_t)stream>>>(*cfg, *bufs, n, cf_stride, need_ldp, need_ltq);
+  const int P = cfg->n_px * cfg->n_py, PB = cfg->n_bx * cfg->n_by;
+  const bool cpu = cfg->index_math == HL_INDEX_MATH_TORCH_CPU;
+  const cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (P <= 192 && PB <= 64) {
+    rc = cpu ? launch_fused<true, 6, 2>(cfg, bufs, n, cf_stride, need_ldp, need_ltq, want_base, smem, st)
+             : launch_fused<false, 6, 2>(cfg, bufs, n, cf_stride, need_ldp, need_ltq, want_base, smem, st);
+  } else {
+    rc = cpu ? launch_fused<true, 8, 8>(cfg, bufs, n, cf_stride, need_ldp, need_ltq, want_base, smem, st)
+             : launch_fused<false, 8, 8>(cfg, bufs, n, cf_stride, need_ldp, need_ltq, want_base, smem, st);
+  }
+  if (rc) return rc;
   HL_CHECK_LAUNCH();
   return HL_OK;
 }

@@ -9,7 +9,8 @@ struct EnvView {
   const float* root;     // 13: pos3 quat_xyzw4 lin3 ang3
   const float* dof;      // 24: (pos, vel) interleaved
   const float* cf;       // B*3 contact forces
-  const float* foot[4];  // 13 each: rigid-body record of foot f (pos [0:3], lin vel [7:10])
+  const float* fpos[4];  // world position (3) of foot f
+  const float* fvel[4];  // world linear velocity (3) of foot f
   const float* act;      // 12 each
   const float* lact;
   const float* llact;
@@ -174,9 +175,9 @@ __device__ __forceinline__ float hl_pose(const HlCfg& c, const EnvView& v, int j
 
 // foot f position / velocity relative to the base, rotated into the body frame (LR:1612-1616,1685-1692)
 __device__ __forceinline__ void hl_foot_body(const EnvView& v, int f, bool vel, float* o) {
-  const int fo = vel ? 7 : 0, ro = vel ? 7 : 0;
-  hl_quat_rotate_inverse(v.root + 3, v.foot[f][fo] - v.root[ro], v.foot[f][fo + 1] - v.root[ro + 1],
-                         v.foot[f][fo + 2] - v.root[ro + 2], o);
+  const float* p = vel ? v.fvel[f] : v.fpos[f];
+  const int ro = vel ? 7 : 0;
+  hl_quat_rotate_inverse(v.root + 3, p[0] - v.root[ro], p[1] - v.root[ro + 1], p[2] - v.root[ro + 2], o);
 }
 
 __device__ __forceinline__ float hl_stumble(const HlCfg& c, const EnvView& v, const EnvScalars& s, float factor) {  // LR:1589-1608
@@ -208,11 +209,11 @@ __device__ float hl_foot_clearance_terrain(const HlCfg& c, const HlEnvBuffers& b
   for (int f = 0; f < 4; ++f) {
     float fh;
     if (c.mesh_type == 0) {
-      fh = v.foot[f][2];
+      fh = v.fpos[f][2];
     } else {
       // the shifted feet_pos is what gets divided (no second +border: the in-place add already
       // happened); coordinates may have been shifted by an earlier foot_clearance_terrain* term
-      float sx = v.foot[f][0], sy = v.foot[f][1], sz = v.foot[f][2];
+      float sx = v.fpos[f][0], sy = v.fpos[f][1], sz = v.fpos[f][2];
       for (int k = 0; k < s.feet_shift; ++k) {
         sx = __fadd_rn(sx, c.border_size);
         sy = __fadd_rn(sy, c.border_size);
@@ -225,7 +226,7 @@ __device__ float hl_foot_clearance_terrain(const HlCfg& c, const HlEnvBuffers& b
       iy = iy < 0 ? 0 : (iy > c.terrain_cols - 2 ? c.terrain_cols - 2 : iy);
       fh = sz - (float)hl_sample_min3(c, b, (int)ix, (int)iy) * c.vertical_scale;
     }
-    const float lat = sqrtf(hl_sq(v.foot[f][7]) + hl_sq(v.foot[f][8]));
+    const float lat = sqrtf(hl_sq(v.fvel[f][0]) + hl_sq(v.fvel[f][1]));
     acc += lat * hl_sq(fh - c.foot_height_target_terrain);
   }
   return acc;

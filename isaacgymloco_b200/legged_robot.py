@@ -176,6 +176,8 @@ class FusedLeggedRobot:
 
     def _stages(self, stages: int, env_ids: Optional[torch.Tensor] = None, n_ids: Optional[torch.Tensor] = None):
         if env_ids is not None and n_ids is None:
+            if env_ids.numel() == 0:
+                return
             env_ids = env_ids.to(self.device, torch.long).contiguous()
             n_ids = torch.tensor([env_ids.numel()], dtype=torch.int32, device=self.device)
         L.check(L.lib.hl_post_physics_stages(ctypes.byref(self._c), ctypes.byref(self._buffers()), stages,
@@ -246,6 +248,8 @@ class FusedLeggedRobot:
     def compute_termination_observations(self, env_ids):
         """LR:439-460 -> (len(env_ids), 238)."""
         env_ids = env_ids.to(self.device, torch.long).contiguous()
+        if env_ids.numel() == 0:
+            return self._term_priv[:0]
         n_ids = torch.tensor([env_ids.numel()], dtype=torch.int32, device=self.device)
         self._terminal_rows(env_ids, n_ids)
         return self._term_priv[:env_ids.numel()]
@@ -271,9 +275,11 @@ class FusedLeggedRobot:
                                           L.ptr(self._n_reset), L.ptr(self._select_ws), L.stream()))
         self._terminal_rows(self._reset_ids, self._n_reset)
 
-    def fused_post_reset(self):
+    def fused_post_reset(self, with_reset_zero: bool = False):
+        """Patch the reset envs after reset_idx.  with_reset_zero=True also applies reset_idx's own
+        RNG-free buffer resets in the kernel (for replay loops that skip the torch reset_idx)."""
         L.check(L.lib.hl_post_reset_fixup(ctypes.byref(self._c), ctypes.byref(self._buffers()), L.ptr(self._reset_ids),
-                                          L.ptr(self._n_reset), self.num_envs, L.stream()))
+                                          L.ptr(self._n_reset), int(with_reset_zero), self.num_envs, L.stream()))
 
     def post_physics_step(self):
         """LR:178-247 -> (env_ids, termination_privileged_obs, terminal_amp_states)."""

@@ -511,9 +511,12 @@ class OracleEnv:
         if len(env_ids) == 0:
             return
         n = self.num_envs
-        self.dof_state.view(n, 12, 2)[env_ids] = targets["dof_state"].view(n, 12, 2)[env_ids]
-        self.root_states[env_ids] = targets["root_states"][env_ids]
-        self.commands[env_ids] = targets["commands"][env_ids]
+        if "dof_state" in targets:
+            self.dof_state.view(n, 12, 2)[env_ids] = targets["dof_state"].view(n, 12, 2)[env_ids]
+        if "root_states" in targets:
+            self.root_states[env_ids] = targets["root_states"][env_ids]
+        if "commands" in targets:
+            self.commands[env_ids] = targets["commands"][env_ids]
         for name in ("last_actions", "last_last_actions", "last_dof_pos", "last_dof_vel",
                      "last_torques", "feet_air_time"):
             getattr(self, name)[env_ids] = 0.0

@@ -215,3 +215,27 @@ def test_philox_noise_statistics():
     assert float(u.max()) <= 1.0 and float(u.min()) >= -1.0
     cols = torch.corrcoef(u[:, :64].T)
     assert float((cols - torch.eye(64)).abs().max()) < 0.08
+
+
+def test_fixup_with_reset_zero_matches_reset_idx_bookkeeping():
+    """Replay mode (bench.py): no torch reset_idx; hl_post_reset_fixup(with_reset_zero=1) applies the
+    RNG-free buffer resets of LR:323-329,350,361 itself.  Two consecutive steps vs the oracle."""
+    from gpu_helpers import assert_close, assert_equal, compare_snapshots, make_env
+    from oracle import torch_oracle as O
+    from isaacgymloco_b200 import config as C, synthetic as S
+    n = 4096
+    cfg = C.aliengo("stairs", num_envs=n)
+    hf = S.make_terrain(cfg, seed=8)
+    state = S.make_state(cfg, n, hf, seed=21)
+    noise = S.make_noise(n, seed=22)
+    oenv = O.OracleEnv(cfg, S.to_device(state, "cuda"), hf.cuda())
+    env = make_env(cfg, state, hf, noise=noise)
+    for step in range(2):
+        oids, _, _ = oenv.post_physics_step(S.to_device(noise, "cuda"), {})   # {}: zero-only reset
+        env.fused_pre_reset()
+        env.fused_post_reset(with_reset_zero=True)
+        env.common_step_counter += 1
+        k = int(env._n_reset.item())
+        assert k > 0
+        assert_equal(env._reset_ids[:k], oids, "env_ids")
+        compare_snapshots(env.snapshot(), oenv.snapshot())
