@@ -66,6 +66,21 @@ __device__ __forceinline__ uint4 hl_noise_block(uint64_t seed, uint64_t offset, 
   return hl_philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 
+__device__ __forceinline__ unsigned hl_pick(const uint4& q, int cpt) { return cpt == 0 ? q.x : (cpt == 1 ? q.y : (cpt == 2 ? q.z : q.w)); }
+
+// Canonical mapping of one env's observation noise onto Philox blocks (stream 0 = observation,
+// 1 = terminal observation), shared by every kernel:
+//   height point p = 32*it + lane    -> component it&3 of block (it>>2)*32 + lane
+//   one-step obs element k = lane    -> component c0   of block cb*32 + lane
+//   one-step obs element k = lane+32 -> component c0+1 of block cb*32 + lane
+// where the last height pass leaves two spare components when ceil(P/32) mod 4 is 1 or 2 (aliengo:
+// P = 187 -> 6 iterations -> cb = 1, c0 = 2); otherwise a further block is drawn.
+__device__ __forceinline__ void hl_cur_noise_slot(int P, int& cb, int& c0) {
+  const int nit = (P + 31) >> 5, rem = nit & 3;
+  if (rem == 1 || rem == 2) { cb = (nit - 1) >> 2; c0 = 2; }
+  else { cb = (nit + 3) >> 2; c0 = 0; }
+}
+
 __device__ __forceinline__ float hl_clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 // torch `%` on floats (Python sign): fmod then fix-up.

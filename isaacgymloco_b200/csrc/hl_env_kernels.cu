@@ -38,8 +38,57 @@ static int check_cfg(const HlCfg* c, const HlEnvBuffers* b) {
 }
 
 // ============================================================================= a1: PD torques
-// LR:658-688.  One thread per (env, dof); dof_state read as float2 (pos, vel).
-__global__ void __launch_bounds__(256) hl_pd_torque_kernel(HlCfg c, const float* __restrict__ actions, long long a_stride,
+// LR:658-688.  One thread per env: 3+6+3 independent 128-bit loads in flight, 3 128-bit stores.
+struct PdCfg {
+  float action_scale, hip_reduction, sim_dt;
+  int control_type;
+  float p_gains[12], d_gains[12], torque_limits[12], default_dof_pos[12];
+};
+__device__ __forceinline__ float pd_one(const PdCfg& c, int d, float action, float ms, float pos, float vel, float kp,
+                                        float kd, float last_vel, float* target) {
+  float scaled = (ms * action) * c.action_scale;
+  if (d % 3 == 0) scaled *= c.hip_reduction;  // columns [0,3,6,9]
+  *target = c.default_dof_pos[d] + scaled;
+  float tq;
+  if (c.control_type == 0) tq = c.p_gains[d] * kp * (*target - pos) - c.d_gains[d] * kd * vel;
+  else if (c.control_type == 1) tq = c.p_gains[d] * (scaled - vel) - c.d_gains[d] * (vel - last_vel) / c.sim_dt;
+  else tq = scaled;
+  return hl_clampf(tq, -c.torque_limits[d], c.torque_limits[d]);
+}
+__global__ void __launch_bounds__(128) hl_pd_torque_vec_kernel(PdCfg c, const float* __restrict__ actions, long long a_stride,
+                                                               const float4* __restrict__ dof_state,
+                                                               const float4* __restrict__ motor_strength,
+                                                               const float* __restrict__ kp, const float* __restrict__ kd,
+                                                               const float4* __restrict__ last_dof_vel, float4* __restrict__ out,
+                                                               float4* __restrict__ target_out, long long n) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const float4* a4 = reinterpret_cast<const float4*>(actions + e * a_stride);
+  float4 a[3], m[3], dv[6], lv[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) a[j] = __ldg(a4 + j);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) m[j] = __ldg(motor_strength + e * 3 + j);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) dv[j] = __ldg(dof_state + e * 6 + j);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) lv[j] = c.control_type == 1 ? __ldg(last_dof_vel + e * 3 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float kpe = __ldg(kp + e), kde = __ldg(kd + e);
+  const float* af = reinterpret_cast<const float*>(a);
+  const float* mf = reinterpret_cast<const float*>(m);
+  const float* df = reinterpret_cast<const float*>(dv);
+  const float* lf = reinterpret_cast<const float*>(lv);
+  float tq[12], tg[12];
+#pragma unroll
+  for (int d = 0; d < 12; ++d) tq[d] = pd_one(c, d, af[d], mf[d], df[2 * d], df[2 * d + 1], kpe, kde, lf[d], &tg[d]);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    out[e * 3 + j] = make_float4(tq[4 * j], tq[4 * j + 1], tq[4 * j + 2], tq[4 * j + 3]);
+    if (target_out) target_out[e * 3 + j] = make_float4(tg[4 * j], tg[4 * j + 1], tg[4 * j + 2], tg[4 * j + 3]);
+  }
+}
+// fallback for unaligned / oddly strided action views: one thread per (env, dof)
+__global__ void __launch_bounds__(256) hl_pd_torque_kernel(PdCfg c, const float* __restrict__ actions, long long a_stride,
                                                            const float2* __restrict__ dof_state,
                                                            const float* __restrict__ motor_strength,
                                                            const float* __restrict__ kp, const float* __restrict__ kd,
@@ -50,21 +99,11 @@ __global__ void __launch_bounds__(256) hl_pd_torque_kernel(HlCfg c, const float*
   if (i >= total) return;
   const long long e = i / 12;
   const int d = (int)(i - e * 12);
-  const float a = motor_strength[i] * actions[e * a_stride + d];
-  float scaled = a * c.action_scale;
-  if (d % 3 == 0) scaled *= c.hip_reduction;  // columns [0,3,6,9]
-  const float target = c.default_dof_pos[d] + scaled;
   const float2 pv = dof_state[i];
-  float tq;
-  if (c.control_type == 0) {
-    tq = c.p_gains[d] * kp[e] * (target - pv.x) - c.d_gains[d] * kd[e] * pv.y;
-  } else if (c.control_type == 1) {
-    tq = c.p_gains[d] * (scaled - pv.y) - c.d_gains[d] * (pv.y - last_dof_vel[i]) / c.sim_dt;
-  } else {
-    tq = scaled;
-  }
-  out[i] = hl_clampf(tq, -c.torque_limits[d], c.torque_limits[d]);
-  if (target_out) target_out[i] = target;
+  float tg;
+  out[i] = pd_one(c, d, actions[e * a_stride + d], motor_strength[i], pv.x, pv.y, kp[e], kd[e],
+                  c.control_type == 1 ? last_dof_vel[i] : 0.0f, &tg);
+  if (target_out) target_out[i] = tg;
 }
 
 extern "C" int hl_pd_torque(const HlCfg* cfg, const float* actions, int64_t a_stride, const float* dof_state,
@@ -74,9 +113,29 @@ extern "C" int hl_pd_torque(const HlCfg* cfg, const float* actions, int64_t a_st
   HL_CHECK_ARG(actions && dof_state && motor_strength && kp && kd && torques_out, "null pointer");
   HL_CHECK_ARG(cfg->control_type != 1 || last_dof_vel, "control_type V needs last_dof_vel");
   if (n <= 0) return HL_OK;
-  const long long total = n * 12;
-  hl_pd_torque_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      *cfg, actions, a_stride, (const float2*)dof_state, motor_strength, kp, kd, last_dof_vel, torques_out, target_out, total);
+  PdCfg pc;
+  pc.action_scale = cfg->action_scale;
+  pc.hip_reduction = cfg->hip_reduction;
+  pc.sim_dt = cfg->sim_dt;
+  pc.control_type = cfg->control_type;
+  for (int d = 0; d < 12; ++d) {
+    pc.p_gains[d] = cfg->p_gains[d];
+    pc.d_gains[d] = cfg->d_gains[d];
+    pc.torque_limits[d] = cfg->torque_limits[d];
+    pc.default_dof_pos[d] = cfg->default_dof_pos[d];
+  }
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  const bool vec = al16(actions) && (a_stride % 4 == 0) && al16(dof_state) && al16(motor_strength) && al16(torques_out) &&
+                   (!target_out || al16(target_out)) && (!last_dof_vel || al16(last_dof_vel));
+  if (vec) {
+    hl_pd_torque_vec_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        pc, actions, a_stride, (const float4*)dof_state, (const float4*)motor_strength, kp, kd, (const float4*)last_dof_vel,
+        (float4*)torques_out, (float4*)target_out, n);
+  } else {
+    const long long total = n * 12;
+    hl_pd_torque_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        pc, actions, a_stride, (const float2*)dof_state, motor_strength, kp, kd, last_dof_vel, torques_out, target_out, total);
+  }
   HL_CHECK_LAUNCH();
   return HL_OK;
 }
@@ -366,20 +425,24 @@ __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, 
           if (k < 225) b.obs_buf_out[e * 270 + 45 + k] = clip ? hl_clampf(old[i], -cl, cl) : old[i];
         }
       }
-      for (int k = lane; k < 45; k += 32) {
-        float u = 0.5f;
-        if (c.add_noise) {
-          if (b.noise_u45) u = b.noise_u45[e * 45 + k];
-          else {
-            const uint4 r = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)s.gid, (unsigned)(k >> 2), 2u);
-            const int cpt = k & 3;
-            u = hl_u01(cpt == 0 ? r.x : (cpt == 1 ? r.y : (cpt == 2 ? r.z : r.w)));
+      {
+        uint4 nb = make_uint4(0u, 0u, 0u, 0u);
+        int cb, c0;
+        hl_cur_noise_slot(P, cb, c0);
+        if (c.add_noise && !b.noise_u45)
+          nb = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)s.gid, (unsigned)(cb * 32 + lane), 0u);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k = lane + 32 * h;
+          if (k < 45) {
+            float u = 0.5f;
+            if (c.add_noise) u = b.noise_u45 ? b.noise_u45[e * 45 + k] : hl_u01(hl_pick(nb, c0 + h));
+            float x = hl_add_noise45(c, hl_obs45(c, v, s, k), u, k);
+            if (clip) x = hl_clampf(x, -cl, cl);
+            b.obs_buf_out[e * 270 + k] = x;
+            b.privileged_obs_buf[e * PD + k] = x;
           }
         }
-        float x = hl_add_noise45(c, hl_obs45(c, v, s, k), u, k);
-        if (clip) x = hl_clampf(x, -cl, cl);
-        b.obs_buf_out[e * 270 + k] = x;
-        b.privileged_obs_buf[e * PD + k] = x;
       }
       if (lane < 6) {
         float x = lane < 3 ? s.blv[lane] * c.obs_lin_vel : b.disturbance[e * B * 3 + (lane - 3)];
@@ -434,7 +497,7 @@ static int launch_stage(const HlCfg* cfg, const HlEnvBuffers* bufs, unsigned sta
   HL_CHECK_ARG((ids == nullptr) == (n_ids == nullptr), "env_ids and n_ids_dev go together");
   if (n <= 0) return HL_OK;
   long long blocks = (n * 32 + 255) / 256;
-  if (ids) blocks = blocks < 148 * 4 ? blocks : 148 * 4;  // id lists are short; grid-stride covers the rest
+  if (ids) blocks = blocks < 148 * 8 ? blocks : 148 * 8;  // id lists are short; grid-stride covers the rest
   hl_stage_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*cfg, *bufs, stages, (const long long*)ids, n_ids, n);
   HL_CHECK_LAUNCH();
   return HL_OK;
@@ -483,17 +546,21 @@ __global__ void __launch_bounds__(256) hl_terminal_rows_kernel(HlCfg c, HlEnvBuf
       s.bav[k] = b.base_ang_vel[e * 3 + k];
       s.pg[k] = b.projected_gravity[e * 3 + k];
     }
-    for (int k = lane; k < 45; k += 32) {
-      float u = 0.5f;
-      if (c.add_noise) {
-        if (u45) u = u45[e * 45 + k];
-        else {
-          const uint4 rr = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)s.gid, (unsigned)(k >> 2), 3u);
-          const int cpt = k & 3;
-          u = hl_u01(cpt == 0 ? rr.x : (cpt == 1 ? rr.y : (cpt == 2 ? rr.z : rr.w)));
+    {
+      uint4 nb = make_uint4(0u, 0u, 0u, 0u);
+      int cb, c0;
+      hl_cur_noise_slot(P, cb, c0);
+      if (c.add_noise && !u45)
+        nb = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)s.gid, (unsigned)(cb * 32 + lane), 1u);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        if (k < 45) {
+          float u = 0.5f;
+          if (c.add_noise) u = u45 ? u45[e * 45 + k] : hl_u01(hl_pick(nb, c0 + h));
+          out_priv[r * PD + k] = hl_add_noise45(c, hl_obs45(c, v, s, k), u, k);
         }
       }
-      out_priv[r * PD + k] = hl_add_noise45(c, hl_obs45(c, v, s, k), u, k);
     }
     if (lane < 6) out_priv[r * PD + 45 + lane] = lane < 3 ? s.blv[lane] * c.obs_lin_vel : b.disturbance[e * B * 3 + (lane - 3)];
     if (c.measure_heights) {
@@ -524,7 +591,7 @@ extern "C" int hl_terminal_rows(const HlCfg* cfg, const HlEnvBuffers* bufs, cons
   if (int r = check_cfg(cfg, bufs)) return r;
   HL_CHECK_ARG(env_ids && n_ids_dev && out_priv, "null pointer");
   if (n <= 0) return HL_OK;
-  hl_terminal_rows_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(*cfg, *bufs, (const long long*)env_ids, n_ids_dev, u45,
+  hl_terminal_rows_kernel<<<(unsigned)((n * 32 + 255) / 256 < 148 * 8 ? (n * 32 + 255) / 256 : 148 * 8), 256, 0, (cudaStream_t)stream>>>(*cfg, *bufs, (const long long*)env_ids, n_ids_dev, u45,
                                                                  u187, out_priv, out_amp, n);
   HL_CHECK_LAUNCH();
   return HL_OK;
@@ -677,27 +744,6 @@ __device__ __forceinline__ void stage_in4(float* dst, const float* __restrict__ 
     dst[e * STRIDE + k] = __ldg(src + idx);
   }
 }
-// runtime record size (contact forces)
-__device__ __forceinline__ void stage_in4_rt(float* dst, int stride, const float* __restrict__ src, int rec, int count, int tid) {
-  const int total = count * rec;
-  const int n4 = total >> 2;
-  const float4* src4 = reinterpret_cast<const float4*>(src);
-  for (int i = tid; i < n4; i += FUSED_THREADS) {
-    const float4 v = __ldg(src4 + i);
-    const int base = i << 2;
-    const float vv[4] = {v.x, v.y, v.z, v.w};
-    int e = base / rec, k = base - e * rec;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      dst[e * stride + k] = vv[j];
-      if (++k == rec) { k = 0; ++e; }
-    }
-  }
-  for (int idx = (n4 << 2) + tid; idx < total; idx += FUSED_THREADS) {
-    const int e = idx / rec, k = idx - e * rec;
-    dst[e * stride + k] = __ldg(src + idx);
-  }
-}
 // shared rows -> global (count x 12 contiguous); rows whose env resets are left to the fix-up
 __device__ __forceinline__ void stage_out12(float* __restrict__ dst, const float* src, int count, int tid,
                                             const unsigned char* skip) {
@@ -742,26 +788,76 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
   float* s_cf = reinterpret_cast<float*>(smem_raw + sizeof(FusedSmem));
   float* s_ldp = s_cf + EPB * cf_stride;
   float* s_ltq = s_ldp + (need_ldp ? EPB * S13 : 0);
+  float* s_sums = s_ltq + (need_ltq ? EPB * S13 : 0);  // (R, EPB) episode sums of this block
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const long long e0 = (long long)blockIdx.x * EPB;
   const int cnt = (int)((n - e0) < EPB ? (n - e0) : EPB);
   const int B = c.num_bodies, P = c.n_px * c.n_py, PD = 51 + P;
 
-  // ---------------- phase 0: stage inputs (float4, coalesced)
-  stage_in4<13, S13>(sm.root, b.root_states + e0 * 13, cnt, tid);
-  stage_in4<24, SDOF>(sm.dof, b.dof_state + e0 * 24, cnt, tid);
-  stage_in4_rt(s_cf, cf_stride, b.contact_forces + e0 * B * 3, B * 3, cnt, tid);
-  for (int i = tid; i < cnt * 24; i += FUSED_THREADS) {  // pos/vel of the 4 foot records only
-    const int e = i / 24, r = i - e * 24, f = r / 6, k = r - f * 6;
-    sm.foot[e * SFOOT + r] = __ldg(b.rigid_body_states + ((e0 + e) * B + c.feet_idx[f]) * 13 + (k < 3 ? k : k + 4));
+  // ---------------- phase 0: stage inputs.  Every load of the block is issued before the first
+  // shared-memory store (all requests in flight at once: ~40 KB per CTA), 128-bit where the slab
+  // is 16-B aligned.
+  const int R = c.n_terms + c.has_termination_term;
+  {
+    const float4* root4 = reinterpret_cast<const float4*>(b.root_states + e0 * 13);
+    const float4* dof4 = reinterpret_cast<const float4*>(b.dof_state + e0 * 24);
+    const float4* cf4p = reinterpret_cast<const float4*>(b.contact_forces + e0 * B * 3);
+    const float4* a4[5] = {reinterpret_cast<const float4*>(b.actions + e0 * 12), reinterpret_cast<const float4*>(b.last_actions + e0 * 12),
+                           reinterpret_cast<const float4*>(b.last_last_actions + e0 * 12),
+                           reinterpret_cast<const float4*>(b.last_dof_vel + e0 * 12), reinterpret_cast<const float4*>(b.torques + e0 * 12)};
+    float* a_dst[5] = {sm.act, sm.lact, sm.llact, sm.ldv, sm.tq};
+    const int n_root = (cnt * 13) >> 2, n_dof = (cnt * 24) >> 2, n_cf = (cnt * B * 3) >> 2, n_a = (cnt * 12) >> 2;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 r_root = tid < n_root ? __ldg(root4 + tid) : z4;
+    float4 r_dof[2], r_cf[4], r_a[5];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) r_dof[j] = tid + j * FUSED_THREADS < n_dof ? __ldg(dof4 + tid + j * FUSED_THREADS) : z4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r_cf[j] = tid + j * FUSED_THREADS < n_cf ? __ldg(cf4p + tid + j * FUSED_THREADS) : z4;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) r_a[j] = tid < n_a ? __ldg(a4[j] + tid) : z4;
+    float r_foot[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {  // pos/vel of the 4 foot records only
+      const int i = tid + j * FUSED_THREADS;
+      const int e = i / 24, r = i - e * 24, f = r / 6, k = r - f * 6;
+      r_foot[j] = i < cnt * 24 ? __ldg(b.rigid_body_states + ((e0 + e) * B + c.feet_idx[f]) * 13 + (k < 3 ? k : k + 4)) : 0.f;
+    }
+    // episode sums rows (R x cnt), coalesced per row
+    for (int i = tid; i < R * EPB; i += FUSED_THREADS) {
+      const int k = i / EPB, e = i - k * EPB;
+      if (e < cnt && b.episode_sums) s_sums[i] = __ldg(b.episode_sums + (long long)k * n + e0 + e);
+    }
+    // commit to shared memory (odd row strides)
+    auto put4 = [](float* dst, int stride, int rec, int i4, const float4& v) {
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      int e = (i4 << 2) / rec, k = (i4 << 2) - e * rec;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dst[e * stride + k] = vv[j];
+        if (++k == rec) { k = 0; ++e; }
+      }
+    };
+    if (tid < n_root) put4(sm.root, S13, 13, tid, r_root);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) if (tid + j * FUSED_THREADS < n_dof) put4(sm.dof, SDOF, 24, tid + j * FUSED_THREADS, r_dof[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (tid + j * FUSED_THREADS < n_cf) put4(s_cf, cf_stride, B * 3, tid + j * FUSED_THREADS, r_cf[j]);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) if (tid < n_a) put4(a_dst[j], S13, 12, tid, r_a[j]);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int i = tid + j * FUSED_THREADS;
+      if (i < cnt * 24) sm.foot[(i / 24) * SFOOT + (i % 24)] = r_foot[j];
+    }
+    // leftovers: contact slabs beyond 4 float4 per thread (num_bodies > 21) and ragged tails
+    for (int i4 = tid + 4 * FUSED_THREADS; i4 < n_cf; i4 += FUSED_THREADS) put4(s_cf, cf_stride, B * 3, i4, __ldg(cf4p + i4));
+    for (int idx = (n_root << 2) + tid; idx < cnt * 13; idx += FUSED_THREADS) sm.root[(idx / 13) * S13 + idx % 13] = __ldg(b.root_states + e0 * 13 + idx);
+    for (int idx = (n_cf << 2) + tid; idx < cnt * B * 3; idx += FUSED_THREADS)
+      s_cf[(idx / (B * 3)) * cf_stride + idx % (B * 3)] = __ldg(b.contact_forces + e0 * B * 3 + idx);
+    if (need_ldp) stage_in4<12, S13>(s_ldp, b.last_dof_pos + e0 * 12, cnt, tid);
+    if (need_ltq) stage_in4<12, S13>(s_ltq, b.last_torques + e0 * 12, cnt, tid);
   }
-  stage_in4<12, S13>(sm.act, b.actions + e0 * 12, cnt, tid);
-  stage_in4<12, S13>(sm.lact, b.last_actions + e0 * 12, cnt, tid);
-  stage_in4<12, S13>(sm.llact, b.last_last_actions + e0 * 12, cnt, tid);
-  stage_in4<12, S13>(sm.ldv, b.last_dof_vel + e0 * 12, cnt, tid);
-  stage_in4<12, S13>(sm.tq, b.torques + e0 * 12, cnt, tid);
-  if (need_ldp) stage_in4<12, S13>(s_ldp, b.last_dof_pos + e0 * 12, cnt, tid);
-  if (need_ltq) stage_in4<12, S13>(s_ltq, b.last_torques + e0 * 12, cnt, tid);
   __syncthreads();
 
   if (wid < SCALAR_WARPS) {
@@ -789,25 +885,45 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
       s.gid = ge + c.env_id_offset;
       s.feet_shift = 0;
       s.base_h = 0.0f;
-      s.terrain_level = b.terrain_levels ? b.terrain_levels[ge] : 0;
-      s.ep_len = b.episode_length_buf[ge] + 1;  // LR:193
+      // independent global loads first (all in flight together)
+      const long long tl = b.terrain_levels ? __ldg(b.terrain_levels + ge) : 0;
+      const long long epl = b.episode_length_buf[ge];
       const float4 cm = reinterpret_cast<const float4*>(b.commands)[ge];
-      s.cmd[0] = cm.x; s.cmd[1] = cm.y; s.cmd[2] = cm.z; s.cmd[3] = cm.w;
       const float4 ar = reinterpret_cast<const float4*>(b.feet_air_time)[ge];
-      s.air[0] = ar.x; s.air[1] = ar.y; s.air[2] = ar.z; s.air[3] = ar.w;
       const unsigned lc4 = reinterpret_cast<const unsigned*>(b.last_contacts)[ge];
+      float* dptr = b.disturbance + ge * B * 3;
+      const float d0 = dptr[0], d1 = dptr[1], d2 = dptr[2];
+      s.terrain_level = tl;
+      s.ep_len = epl + 1;  // LR:193
+      s.cmd[0] = cm.x; s.cmd[1] = cm.y; s.cmd[2] = cm.z; s.cmd[3] = cm.w;
+      s.air[0] = ar.x; s.air[1] = ar.y; s.air[2] = ar.z; s.air[3] = ar.w;
       unsigned last = 0;
 #pragma unroll
       for (int f = 0; f < 4; ++f) last |= (((lc4 >> (8 * f)) & 0xffu) ? 1u : 0u) << f;
       hl_frame(v, s);
       hl_contacts(c, v, last, s);
       if (c.heading_command) s.cmd[2] = hl_heading_command(v.root + 3, s.cmd[3]);
+      // one-step observation without noise (the scan warps add noise, clip and store it)
+      float* cur = sm.cur + e * SCUR;
+#pragma unroll
+      for (int k = 0; k < 45; ++k) cur[k] = hl_obs45(c, v, s, k);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) cur[45 + k] = s.blv[k] * c.obs_lin_vel;
+      cur[48] = d0; cur[49] = d1; cur[50] = d2;
+    }
+    __threadfence_block();
+    named_bar_arrive(2, FUSED_THREADS);  // sm.cur is ready for the scan warps
+    if (act_lane) {
       hl_check_termination(c, v, s);
       b.episode_length_buf[ge] = s.ep_len;
       b.commands[ge * 4 + 2] = s.cmd[2];
       b.reset_buf[ge] = s.reset;
       b.time_out_buf[ge] = s.time_out;
       sm.reset[e] = s.reset;
+      if (!s.reset) {  // LR:235; reset envs: the fix-up still reads the disturbance, then zeroes it
+        float* dptr = b.disturbance + ge * B * 3;
+        dptr[0] = 0.0f; dptr[1] = 0.0f; dptr[2] = 0.0f;
+      }
       unsigned cf4 = 0;
 #pragma unroll
       for (int f = 0; f < 4; ++f) cf4 |= ((s.cfilt >> f) & 1u) << (8 * f);
@@ -818,38 +934,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
         b.base_ang_vel[ge * 3 + k] = s.bav[k];
         b.projected_gravity[ge * 3 + k] = s.pg[k];
       }
-      // one-step observation (+noise), clipped: LR:385-394,167-171
-      float* cur = sm.cur + e * SCUR;
-      const float cl = c.clip_obs;
-      if (c.add_noise && !b.noise_u45) {
-#pragma unroll 1
-        for (int kb = 0; kb < 12; ++kb) {
-          const uint4 r = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)s.gid, (unsigned)kb, 2u);
-          const unsigned rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int k = kb * 4 + j;
-            if (k < 45) cur[k] = hl_clampf(hl_add_noise45(c, hl_obs45(c, v, s, k), hl_u01(rr[j]), k), -cl, cl);
-          }
-        }
-      } else {
-        for (int k = 0; k < 45; ++k) {
-          const float u = (c.add_noise && b.noise_u45) ? b.noise_u45[ge * 45 + k] : 0.5f;
-          cur[k] = hl_clampf(hl_add_noise45(c, hl_obs45(c, v, s, k), u, k), -cl, cl);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        cur[45 + k] = hl_clampf(s.blv[k] * c.obs_lin_vel, -cl, cl);
-        float* dptr = b.disturbance + ge * B * 3 + k;
-        cur[48 + k] = hl_clampf(*dptr, -cl, cl);
-        if (!s.reset) *dptr = 0.0f;  // LR:235; reset envs: the fix-up still reads it, then zeroes it
-      }
     }
     if (want_base) named_bar_sync(1, FUSED_THREADS);  // base heights are in shared memory
     if (act_lane) {
       s.base_h = sm.base_h[e];
-      const float rew = hl_compute_reward(c, b, v, s, b.episode_sums ? b.episode_sums + ge : nullptr, n, true);
+      const float rew = hl_compute_reward(c, b, v, s, b.episode_sums ? s_sums + e : nullptr, EPB, true);
       b.rew_buf[ge] = rew;
       unsigned lc = 0;
 #pragma unroll
@@ -858,12 +947,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
       reinterpret_cast<float4*>(b.feet_air_time)[ge] = make_float4(s.air[0], s.air[1], s.air[2], s.air[3]);
     }
   } else {
-    // ---------------- phase 1b: height scans, one warp per env
+    // ---------------- phase 1b: one warp per env: scans + every row-shaped output of the env
     const int sw = wid - SCALAR_WARPS;
     const int16_t* __restrict__ min3 = b.height_min3;
     const int pitch = c.terrain_cols - 1;
     const bool plane = c.mesh_type == 0;
-    // this lane's grid points (body frame), fixed for the whole kernel
+    // this lane's grid points (body frame) and noise scales, fixed for the whole kernel
     float gx[NIT], gy[NIT], hx[NBIT], hy[NBIT];
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
@@ -878,6 +967,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
       hx[it] = c.bx[i];
       hy[it] = c.by[j];
     }
+    const float nv0 = c.add_noise ? c.noise45[lane] : 0.0f;
+    const float nv1 = (c.add_noise && lane < 13) ? c.noise45[32 + lane] : 0.0f;
+    int cb, c0;
+    hl_cur_noise_slot(P, cb, c0);
     // yaw quaternions of this warp's envs: lane l normalises env sw + SCAN_WARPS*l, broadcast later
     float qz_l = 0.0f, qw_l = 1.0f;
     {
@@ -890,9 +983,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
         const float* root = sm.root + e * S13;
         const float posx = root[0], posy = root[1], posz = root[2];
         float acc = 0.0f;
-        if (plane) {
-          acc = lane == 0 ? posz * (float)PB : 0.0f;
-        } else {
+        if (!plane) {
           int hraw[NBIT];
 #pragma unroll
           for (int it = 0; it < NBIT; ++it) hraw[it] = scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, posx, posy, hx[it], hy[it]);
@@ -907,24 +998,51 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
       named_bar_arrive(1, FUSED_THREADS);
     }
     const bool philox = c.add_noise && !b.noise_u187;
+    const bool philox45 = c.add_noise && !b.noise_u45;
     const float cl = c.clip_obs;
-    for (int li = 0, e = sw; e < cnt; e += SCAN_WARPS, ++li) {
-      const long long ge = e0 + e;
-      const float qz = __shfl_sync(0xffffffffu, qz_l, li), qw = __shfl_sync(0xffffffffu, qw_l, li);
-      const float* root = sm.root + e * S13;
-      const float posx = root[0], posy = root[1], posz = root[2];
-      int hraw[NIT];
+    constexpr int NPASS = (NIT + 3) / 4;
+    // software pipeline: the gathers of the next env are in flight while this one is written out
+    int hnext[NIT];
+    {
+      const float* root = sm.root + sw * S13;
+      const float qz = __shfl_sync(0xffffffffu, qz_l, 0), qw = __shfl_sync(0xffffffffu, qw_l, 0);
 #pragma unroll
       for (int it = 0; it < NIT; ++it)
-        hraw[it] = plane ? 0 : scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, posx, posy, gx[it], gy[it]);
-      uint4 nz[(NIT + 3) / 4];
-      if (philox) {
+        hnext[it] = (plane || sw >= cnt) ? 0 : scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, root[0], root[1], gx[it], gy[it]);
+    }
+    named_bar_sync(2, FUSED_THREADS);  // one-step observations are in shared memory
+    for (int li = 0, e = sw; e < cnt; e += SCAN_WARPS, ++li) {
+      const long long ge = e0 + e;
+      // obs history of this env (independent of everything else): loads first
+      const float* src = b.obs_buf_in + ge * 270;
+      float* dst = b.obs_buf_out + ge * 270;
+      float old[8];
 #pragma unroll
-        for (int a = 0; a < (NIT + 3) / 4; ++a)
+      for (int i = 0; i < 8; ++i) {
+        const int k = i * 32 + lane;
+        old[i] = k < 225 ? src[k] : 0.0f;
+      }
+      int hraw[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) hraw[it] = hnext[it];
+      const int en = e + SCAN_WARPS;
+      if (en < cnt && !plane) {
+        const float* rootn = sm.root + en * S13;
+        const float qz = __shfl_sync(0xffffffffu, qz_l, li + 1), qw = __shfl_sync(0xffffffffu, qw_l, li + 1);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) hnext[it] = scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, rootn[0], rootn[1], gx[it], gy[it]);
+      }
+      const float posz = sm.root[e * S13 + 2];
+      uint4 nz[NPASS + 1];
+      if (philox || philox45) {
+#pragma unroll
+        for (int a = 0; a < NPASS; ++a)
           nz[a] = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)(ge + c.env_id_offset), (unsigned)(a * 32 + lane), 0u);
+        if (cb >= NPASS)
+          nz[NPASS] = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)(ge + c.env_id_offset), (unsigned)(cb * 32 + lane), 0u);
       }
       float* mrow = b.measured_heights + ge * P;
-      float* prow = b.privileged_obs_buf + ge * PD + 51;
+      float* prow = b.privileged_obs_buf + ge * PD;
       const float* urow = b.noise_u187 ? b.noise_u187 + ge * P : nullptr;
 #pragma unroll
       for (int it = 0; it < NIT; ++it) {
@@ -932,46 +1050,49 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
         if (p < P) {
           const float mh = (float)hraw[it] * c.vertical_scale;
           float u = 0.5f;
-          if (philox) {
-            const uint4 q = nz[it >> 2];
-            u = hl_u01((it & 3) == 0 ? q.x : ((it & 3) == 1 ? q.y : ((it & 3) == 2 ? q.z : q.w)));
-          } else if (urow) {
-            u = urow[p];
-          }
+          if (philox) u = hl_u01(hl_pick(nz[it >> 2], it & 3));
+          else if (urow) u = urow[p];
           mrow[p] = mh;
-          prow[p] = hl_clampf(hl_obs_height(c, posz, mh, u), -cl, cl);
+          prow[51 + p] = hl_clampf(hl_obs_height(c, posz, mh, u), -cl, cl);
         }
+      }
+      // slot 0 of obs_buf and privileged_obs[0:51]: noise, clip (LR:394,167-171)
+      {
+        const float* cur = sm.cur + e * SCUR;
+        float x0 = cur[lane], x1 = lane < 19 ? cur[32 + lane] : 0.0f;
+        float u0 = 0.5f, u1 = 0.5f;
+        if (philox45) {
+          const uint4 q = nz[cb < NPASS ? cb : NPASS];
+          u0 = hl_u01(hl_pick(q, c0));
+          u1 = hl_u01(hl_pick(q, c0 + 1));
+        } else if (b.noise_u45) {
+          u0 = b.noise_u45[ge * 45 + lane];
+          if (lane < 13) u1 = b.noise_u45[ge * 45 + 32 + lane];
+        }
+        x0 = hl_clampf(x0 + (2.0f * u0 - 1.0f) * nv0, -cl, cl);
+        x1 = hl_clampf(x1 + (2.0f * u1 - 1.0f) * nv1, -cl, cl);
+        dst[lane] = x0;
+        prow[lane] = x0;
+        if (lane < 13) dst[32 + lane] = x1;
+        if (lane < 19) prow[32 + lane] = x1;
+      }
+      // history shift (register-staged: in-place safe); LR:168 clips the whole buffer
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = i * 32 + lane;
+        if (k < 225) dst[45 + k] = hl_clampf(old[i], -cl, cl);
       }
     }
   }
   __syncthreads();
 
-  // ---------------- phase 2: stores
-  for (int e = wid; e < cnt; e += FUSED_THREADS / 32) {
-    const long long ge = e0 + e;
-    const float* src = b.obs_buf_in + ge * 270;
-    float* dst = b.obs_buf_out + ge * 270;
-    float old[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = i * 32 + lane;
-      old[i] = k < 225 ? src[k] : 0.0f;
+  // ---------------- phase 2: episode sums write-back and the end-of-step roll
+  if (b.episode_sums)
+    for (int i = tid; i < R * EPB; i += FUSED_THREADS) {
+      const int k = i / EPB, e = i - k * EPB;
+      if (e < cnt) b.episode_sums[(long long)k * n + e0 + e] = s_sums[i];
     }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = i * 32 + lane;
-      if (k < 225) dst[45 + k] = hl_clampf(old[i], -c.clip_obs, c.clip_obs);  // LR:168 clips the whole buffer
-    }
-    const float* cur = sm.cur + e * SCUR;
-    float* priv = b.privileged_obs_buf + ge * PD;
-    for (int k = lane; k < 51; k += 32) {
-      const float x = cur[k];
-      if (k < 45) dst[k] = x;
-      priv[k] = x;
-    }
-  }
-  // end-of-step roll (LR:235-241) for the envs that do not reset
+  // LR:235-241 for the envs that do not reset
   stage_out12(b.last_last_actions + e0 * 12, sm.lact, cnt, tid, sm.reset);
   stage_out12(b.last_actions + e0 * 12, sm.act, cnt, tid, sm.reset);
   stage_out12(b.last_torques + e0 * 12, sm.tq, cnt, tid, sm.reset);
@@ -1034,7 +1155,8 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
     need_ltq |= cfg->term_id[k] == T_torques_dif;
     want_base |= cfg->term_id[k] == T_base_height || cfg->term_id[k] == T_base_height_up;
   }
-  const size_t smem = sizeof(FusedSmem) + (size_t)EPB * (cf_stride + (need_ldp ? S13 : 0) + (need_ltq ? S13 : 0)) * sizeof(float);
+  const size_t smem = sizeof(FusedSmem) + (size_t)EPB * (cf_stride + (need_ldp ? S13 : 0) + (need_ltq ? S13 : 0) +
+                                                          cfg->n_terms + cfg->has_termination_term) * sizeof(float);
   HL_CHECK_ARG(smem <= 200 * 1024, "num_bodies too large for the shared-memory slab");
   const int P = cfg->n_px * cfg->n_py, PB = cfg->n_bx * cfg->n_by;
   const bool cpu = cfg->index_math == HL_INDEX_MATH_TORCH_CPU;

@@ -380,7 +380,8 @@ __device__ float hl_eval_term(int id, const HlCfg& c, const HlEnvBuffers& b, con
   return r;
 }
 
-// compute_reward() for one env (LR:363-380).  `sums` points at episode_sums[0][e]; row stride n.
+// compute_reward() for one env (LR:363-380).  `sums` points at this env's column of the (R, n)
+// episode-sums matrix (row stride n).
 // `write` = this thread owns the stores.
 __device__ __forceinline__ float hl_compute_reward(const HlCfg& c, const HlEnvBuffers& b, const EnvView& v, EnvScalars& s,
                                                    float* sums, long long n, bool write) {
