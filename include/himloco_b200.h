@@ -107,9 +107,11 @@ typedef struct HlCfg {
 } HlCfg;
 
 /* Device buffers of one env shard, named after the LeggedRobot attributes they are. */
+#define HL_BUF_HISTORY_CLIPPED 1u /* obs_buf_in already lies within +-clip_observations (true after any step) */
+
 typedef struct HlEnvBuffers {
   int32_t struct_bytes;
-  int32_t _pad;
+  uint32_t flags;                 /* HL_BUF_* */
   /* PhysX state (read-only), LR:929-944 */
   const float* root_states;       /* (N,13)  pos3 quat_xyzw4 lin3 ang3 */
   const float* dof_state;         /* (N,12,2) interleaved pos,vel      */

@@ -18,7 +18,7 @@ _vp = c_void_p
 
 class HlEnvBuffers(ctypes.Structure):
     """Mirror of `struct HlEnvBuffers` (keep field order identical to the header)."""
-    _fields_ = [("struct_bytes", c_int32), ("_pad", c_int32)] + [(n, _vp) for n in (
+    _fields_ = [("struct_bytes", c_int32), ("flags", c_uint32)] + [(n, _vp) for n in (
         "root_states", "dof_state", "contact_forces", "rigid_body_states", "height_samples",
         "height_min3", "actions", "last_actions", "last_last_actions", "last_dof_pos", "last_dof_vel",
         "torques", "last_torques", "last_root_vel", "commands", "episode_length_buf", "last_contacts",

@@ -56,6 +56,30 @@ __device__ __forceinline__ uint4 hl_philox4x32_10(uint4 c, uint2 k) {
   }
   return c;
 }
+// Same function with the 10 round keys precomputed (they depend on the seed only).
+struct HlPhiloxKeys {
+  uint32_t kx[10], ky[10];
+  __device__ __forceinline__ void init(uint64_t seed) {
+    uint32_t x = (uint32_t)seed, y = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      kx[r] = x;
+      ky[r] = y;
+      x += 0x9E3779B9u;
+      y += 0xBB67AE85u;
+    }
+  }
+};
+__device__ __forceinline__ uint4 hl_philox4x32_10(uint4 c, const HlPhiloxKeys& k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.kx[r], lo1, hi0 ^ c.w ^ k.ky[r], lo0);
+  }
+  return c;
+}
+
 __device__ __forceinline__ float hl_u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
 // one Philox block = 4 uniforms for (env, block index, stream, step)
@@ -64,6 +88,13 @@ __device__ __forceinline__ uint4 hl_noise_block(uint64_t seed, uint64_t offset, 
   const uint4 ctr = make_uint4(block | (stream << 24), (uint32_t)env, (uint32_t)(env >> 32) ^ (uint32_t)(offset >> 32),
                                (uint32_t)offset);
   return hl_philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+__device__ __forceinline__ uint4 hl_noise_block(const HlPhiloxKeys& keys, uint64_t offset, uint64_t env, uint32_t block,
+                                                uint32_t stream) {
+  const uint4 ctr = make_uint4(block | (stream << 24), (uint32_t)env, (uint32_t)(env >> 32) ^ (uint32_t)(offset >> 32),
+                               (uint32_t)offset);
+  return hl_philox4x32_10(ctr, keys);
 }
 
 __device__ __forceinline__ unsigned hl_pick(const uint4& q, int cpt) { return cpt == 0 ? q.x : (cpt == 1 ? q.y : (cpt == 2 ? q.z : q.w)); }

@@ -744,15 +744,6 @@ __device__ __forceinline__ void stage_in4(float* dst, const float* __restrict__ 
     dst[e * STRIDE + k] = __ldg(src + idx);
   }
 }
-// shared rows -> global (count x 12 contiguous); rows whose env resets are left to the fix-up
-__device__ __forceinline__ void stage_out12(float* __restrict__ dst, const float* src, int count, int tid,
-                                            const unsigned char* skip) {
-  for (int i = tid; i < count * 12; i += FUSED_THREADS) {
-    const int e = i / 12, k = i - e * 12;
-    if (!skip[e]) dst[i] = src[e * S13 + k];
-  }
-}
-
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -765,8 +756,12 @@ __device__ __forceinline__ int cell32(float world, float border, float hs, float
   return min(max(__float2int_rz(g), 0), hi);
 }
 
-// raw min-of-3 height (int16 units) under body-frame point (bx,by): the reference's op order,
-// every product/sum rounded separately (see hl_scan_axis_* in hl_math.cuh)
+// raw min-of-3 height (int16 units) under body-frame point (bx,by): quat_apply_yaw + translate +
+// border + scale + trunc + clip (LR:1339-1347) in the reference's op order, every product and sum
+// rounded on its own with the non-contractable __fmul_rn/__fadd_rn (see hl_scan_axis_* in
+// hl_math.cuh for the derivation).  NOTE: packed FFMA2 arithmetic was tried here and rejected:
+// ptxas contracts packed mul->add chains into single-rounding FFMA2s even from explicit
+// fma.rn.f32x2 and with -fmad=false, which breaks the one-rounding-per-op guarantee.
 template <bool CPU_MATH>
 __device__ __forceinline__ int scan_gather(const HlCfg& c, const int16_t* __restrict__ min3, int pitch, float qz, float qw,
                                            float posx, float posy, float bx, float by) {
@@ -777,12 +772,18 @@ __device__ __forceinline__ int scan_gather(const HlCfg& c, const int16_t* __rest
   const float ry = __fadd_rn(__fadd_rn(by, ay), cy);
   const int ix = cell32<CPU_MATH>(__fadd_rn(rx, posx), c.border_size, c.horizontal_scale, c.inv_horizontal_scale, c.terrain_rows - 2);
   const int iy = cell32<CPU_MATH>(__fadd_rn(ry, posy), c.border_size, c.horizontal_scale, c.inv_horizontal_scale, c.terrain_cols - 2);
-  return (int)__ldg(min3 + ix * pitch + iy);
+  return (int)__ldg(min3 + (unsigned)(ix * pitch + iy));
 }
 
-template <bool CPU_MATH, int NIT, int NBIT>
-__global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel(HlCfg c, HlEnvBuffers b, long long n, int cf_stride,
-                                                                                 int need_ldp, int need_ltq, int want_base) {
+struct FusedArgs {
+  int cf_stride, need_ldp, need_ltq, want_base;
+  int hist_clipped;       // obs history is known to be within +-clip_obs already (every step after the first)
+  HlPhiloxKeys keys;      // Philox round keys of bufs.philox_seed (host-computed: constant-bank operands)
+};
+
+template <bool CPU_MATH, int NIT, int NBIT, bool HCLIP>
+__global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel(HlCfg c, HlEnvBuffers b, long long n, FusedArgs fa) {
+  const int cf_stride = fa.cf_stride, need_ldp = fa.need_ldp, need_ltq = fa.need_ltq, want_base = fa.want_base;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
   float* s_cf = reinterpret_cast<float*>(smem_raw + sizeof(FusedSmem));
@@ -842,7 +843,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
 #pragma unroll
     for (int j = 0; j < 2; ++j) if (tid + j * FUSED_THREADS < n_dof) put4(sm.dof, SDOF, 24, tid + j * FUSED_THREADS, r_dof[j]);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) if (tid + j * FUSED_THREADS < n_cf) put4(s_cf, cf_stride, B * 3, tid + j * FUSED_THREADS, r_cf[j]);
+    for (int j = 0; j < 4; ++j)
+      if (tid + j * FUSED_THREADS < n_cf) {
+        if (B == 17) put4(s_cf, 51, 51, tid + j * FUSED_THREADS, r_cf[j]);  // aliengo: constant divisor
+        else put4(s_cf, cf_stride, B * 3, tid + j * FUSED_THREADS, r_cf[j]);
+      }
 #pragma unroll
     for (int j = 0; j < 5; ++j) if (tid < n_a) put4(a_dst[j], S13, 12, tid, r_a[j]);
 #pragma unroll
@@ -954,19 +959,22 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
     const bool plane = c.mesh_type == 0;
     // this lane's grid points (body frame) and noise scales, fixed for the whole kernel
     float gx[NIT], gy[NIT], hx[NBIT], hy[NBIT];
+    // p / n via float reciprocal: exact for p < 256 (checked on the host: P, PB <= 256)
+    const float inv_npy = 1.0f / (float)c.n_py, inv_nby = 1.0f / (float)c.n_by;
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
-      const int p = min(it * 32 + lane, P - 1), i = p / c.n_py, j = p - i * c.n_py;
+      const int p = min(it * 32 + lane, P - 1), i = (int)(((float)p + 0.5f) * inv_npy), j = p - i * c.n_py;
       gx[it] = c.px[i];
       gy[it] = c.py[j];
     }
     const int PB = c.n_bx * c.n_by;
 #pragma unroll
     for (int it = 0; it < NBIT; ++it) {
-      const int p = min(it * 32 + lane, PB - 1), i = p / c.n_by, j = p - i * c.n_by;
+      const int p = min(it * 32 + lane, PB - 1), i = (int)(((float)p + 0.5f) * inv_nby), j = p - i * c.n_by;
       hx[it] = c.bx[i];
       hy[it] = c.by[j];
     }
+    const HlPhiloxKeys& keys = fa.keys;
     const float nv0 = c.add_noise ? c.noise45[lane] : 0.0f;
     const float nv1 = (c.add_noise && lane < 13) ? c.noise45[32 + lane] : 0.0f;
     int cb, c0;
@@ -1001,27 +1009,34 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
     const bool philox45 = c.add_noise && !b.noise_u45;
     const float cl = c.clip_obs;
     constexpr int NPASS = (NIT + 3) / 4;
+    // height obs = clamp(z - 0.5 - h, +-1) * s + (2u - 1) * nh  (LR:399-400); with u = k * 2^-24 the
+    // noise is one FFMA: k * (nh * 2^-23) - nh.  |value| <= s + nh, so the +-clip_obs clip of step()
+    // is dropped when it cannot bind.
+    const float nh = c.add_noise ? c.noise_height : 0.0f;
+    const float nh_scale = nh * (1.0f / 8388608.0f);
     // software pipeline: the gathers of the next env are in flight while this one is written out
     int hnext[NIT];
     {
       const float* root = sm.root + sw * S13;
       const float qz = __shfl_sync(0xffffffffu, qz_l, 0), qw = __shfl_sync(0xffffffffu, qw_l, 0);
+      const float px0 = root[0], py0 = root[1];
 #pragma unroll
       for (int it = 0; it < NIT; ++it)
-        hnext[it] = (plane || sw >= cnt) ? 0 : scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, root[0], root[1], gx[it], gy[it]);
+        hnext[it] = (plane || sw >= cnt) ? 0 : scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, px0, py0, gx[it], gy[it]);
     }
     named_bar_sync(2, FUSED_THREADS);  // one-step observations are in shared memory
     for (int li = 0, e = sw; e < cnt; e += SCAN_WARPS, ++li) {
       const long long ge = e0 + e;
-      // obs history of this env (independent of everything else): loads first
-      const float* src = b.obs_buf_in + ge * 270;
-      float* dst = b.obs_buf_out + ge * 270;
+      // row pointers of this env, lane offset folded in (64-bit math once per env)
+      const float* hsrc = b.obs_buf_in + ge * 270 + lane;
+      float* hdst = b.obs_buf_out + ge * 270 + lane;
+      float* mptr = b.measured_heights + ge * P + lane;
+      float* pptr = b.privileged_obs_buf + ge * PD + lane;
+      // obs history (independent of everything else): loads first
       float old[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = i * 32 + lane;
-        old[i] = k < 225 ? src[k] : 0.0f;
-      }
+      for (int i = 0; i < 7; ++i) old[i] = hsrc[i * 32];
+      old[7] = lane < 1 ? hsrc[224] : 0.0f;
       int hraw[NIT];
 #pragma unroll
       for (int it = 0; it < NIT; ++it) hraw[it] = hnext[it];
@@ -1029,31 +1044,32 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
       if (en < cnt && !plane) {
         const float* rootn = sm.root + en * S13;
         const float qz = __shfl_sync(0xffffffffu, qz_l, li + 1), qw = __shfl_sync(0xffffffffu, qw_l, li + 1);
+        const float pxn = rootn[0], pyn = rootn[1];
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) hnext[it] = scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, rootn[0], rootn[1], gx[it], gy[it]);
+        for (int it = 0; it < NIT; ++it) hnext[it] = scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, pxn, pyn, gx[it], gy[it]);
       }
-      const float posz = sm.root[e * S13 + 2];
-      uint4 nz[NPASS + 1];
+      const float rz05 = sm.root[e * S13 + 2] - 0.5f;
+      uint4 nz[NPASS];
+      uint4 nzx = make_uint4(0u, 0u, 0u, 0u);
       if (philox || philox45) {
+        const unsigned long long genv = (unsigned long long)(ge + c.env_id_offset);
 #pragma unroll
-        for (int a = 0; a < NPASS; ++a)
-          nz[a] = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)(ge + c.env_id_offset), (unsigned)(a * 32 + lane), 0u);
-        if (cb >= NPASS)
-          nz[NPASS] = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)(ge + c.env_id_offset), (unsigned)(cb * 32 + lane), 0u);
+        for (int a = 0; a < NPASS; ++a) nz[a] = hl_noise_block(keys, b.philox_offset, genv, (unsigned)(a * 32 + lane), 0u);
+        if (cb >= NPASS) nzx = hl_noise_block(keys, b.philox_offset, genv, (unsigned)(cb * 32 + lane), 0u);
       }
-      float* mrow = b.measured_heights + ge * P;
-      float* prow = b.privileged_obs_buf + ge * PD;
-      const float* urow = b.noise_u187 ? b.noise_u187 + ge * P : nullptr;
+      const float* urow = b.noise_u187 ? b.noise_u187 + ge * P + lane : nullptr;
 #pragma unroll
       for (int it = 0; it < NIT; ++it) {
-        const int p = it * 32 + lane;
-        if (p < P) {
+        // only the last iteration can run past P on the fast path (host guarantees P > 32*(NIT-1) there)
+        if (it < NIT - 1 && NIT == 6 ? true : (it * 32 + lane < P)) {
           const float mh = (float)hraw[it] * c.vertical_scale;
-          float u = 0.5f;
-          if (philox) u = hl_u01(hl_pick(nz[it >> 2], it & 3));
-          else if (urow) u = urow[p];
-          mrow[p] = mh;
-          prow[51 + p] = hl_clampf(hl_obs_height(c, posz, mh, u), -cl, cl);
+          float nzv;
+          if (philox) nzv = fmaf((float)(hl_pick(nz[it >> 2], it & 3) >> 8), nh_scale, -nh);
+          else nzv = urow ? (2.0f * urow[it * 32] - 1.0f) * nh : 0.0f;
+          float hv = fmaf(hl_clampf(rz05 - mh, -1.0f, 1.0f), c.obs_height, nzv);
+          if (HCLIP) hv = hl_clampf(hv, -cl, cl);
+          mptr[it * 32] = mh;
+          pptr[51 + it * 32] = hv;
         }
       }
       // slot 0 of obs_buf and privileged_obs[0:51]: noise, clip (LR:394,167-171)
@@ -1062,7 +1078,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
         float x0 = cur[lane], x1 = lane < 19 ? cur[32 + lane] : 0.0f;
         float u0 = 0.5f, u1 = 0.5f;
         if (philox45) {
-          const uint4 q = nz[cb < NPASS ? cb : NPASS];
+          uint4 q = nzx;
+#pragma unroll
+          for (int a = 0; a < NPASS; ++a)
+            if (cb == a) q = nz[a];
           u0 = hl_u01(hl_pick(q, c0));
           u1 = hl_u01(hl_pick(q, c0 + 1));
         } else if (b.noise_u45) {
@@ -1071,17 +1090,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
         }
         x0 = hl_clampf(x0 + (2.0f * u0 - 1.0f) * nv0, -cl, cl);
         x1 = hl_clampf(x1 + (2.0f * u1 - 1.0f) * nv1, -cl, cl);
-        dst[lane] = x0;
-        prow[lane] = x0;
-        if (lane < 13) dst[32 + lane] = x1;
-        if (lane < 19) prow[32 + lane] = x1;
+        hdst[0] = x0;
+        pptr[0] = x0;
+        if (lane < 13) hdst[32] = x1;
+        if (lane < 19) pptr[32] = x1;
       }
       // history shift (register-staged: in-place safe); LR:168 clips the whole buffer
+      if (!fa.hist_clipped) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = i * 32 + lane;
-        if (k < 225) dst[45 + k] = hl_clampf(old[i], -cl, cl);
+        for (int i = 0; i < 8; ++i) old[i] = hl_clampf(old[i], -cl, cl);
       }
+#pragma unroll
+      for (int i = 0; i < 7; ++i) hdst[45 + i * 32] = old[i];
+      if (lane < 1) hdst[45 + 224] = old[7];
     }
   }
   __syncthreads();
@@ -1092,20 +1113,25 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
       const int k = i / EPB, e = i - k * EPB;
       if (e < cnt) b.episode_sums[(long long)k * n + e0 + e] = s_sums[i];
     }
-  // LR:235-241 for the envs that do not reset
-  stage_out12(b.last_last_actions + e0 * 12, sm.lact, cnt, tid, sm.reset);
-  stage_out12(b.last_actions + e0 * 12, sm.act, cnt, tid, sm.reset);
-  stage_out12(b.last_torques + e0 * 12, sm.tq, cnt, tid, sm.reset);
-  for (int i = tid; i < cnt * 12; i += FUSED_THREADS) {
-    const int e = i / 12, d = i - e * 12;
-    if (sm.reset[e]) continue;
-    b.last_dof_pos[e0 * 12 + i] = sm.dof[e * SDOF + 2 * d];
-    b.last_dof_vel[e0 * 12 + i] = sm.dof[e * SDOF + 2 * d + 1];
-  }
-  for (int i = tid; i < cnt * 6; i += FUSED_THREADS) {
-    const int e = i / 6, k = i - e * 6;
-    if (sm.reset[e]) continue;
-    b.last_root_vel[e0 * 6 + i] = sm.root[e * S13 + 7 + k];
+  // LR:235-241 for the envs that do not reset: one 128-bit store per (env, third of a row)
+  if (tid < cnt * 3) {
+    const int e = tid / 3, q = tid - e * 3;
+    if (!sm.reset[e]) {
+      const int so = e * S13 + q * 4;
+      const long long go = (e0 + e) * 3 + q;
+      reinterpret_cast<float4*>(b.last_last_actions)[go] = make_float4(sm.lact[so], sm.lact[so + 1], sm.lact[so + 2], sm.lact[so + 3]);
+      reinterpret_cast<float4*>(b.last_actions)[go] = make_float4(sm.act[so], sm.act[so + 1], sm.act[so + 2], sm.act[so + 3]);
+      reinterpret_cast<float4*>(b.last_torques)[go] = make_float4(sm.tq[so], sm.tq[so + 1], sm.tq[so + 2], sm.tq[so + 3]);
+      const float* d = sm.dof + e * SDOF + q * 8;
+      reinterpret_cast<float4*>(b.last_dof_pos)[go] = make_float4(d[0], d[2], d[4], d[6]);
+      reinterpret_cast<float4*>(b.last_dof_vel)[go] = make_float4(d[1], d[3], d[5], d[7]);
+      if (q < 2) {  // last_root_vel: 6 floats per env = 3 float2
+        const float* rv = sm.root + e * S13 + 7;
+        float2* dst2 = reinterpret_cast<float2*>(b.last_root_vel) + (e0 + e) * 3;
+        dst2[q] = make_float2(rv[2 * q], rv[2 * q + 1]);
+        if (q == 0) dst2[2] = make_float2(rv[4], rv[5]);
+      }
+    }
   }
   if (b.feet_pos || b.feet_vel) {
     for (int i = tid; i < cnt * 12; i += FUSED_THREADS) {
@@ -1116,10 +1142,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
   }
 }
 
-template <bool CPU_MATH, int NIT, int NBIT>
-static int launch_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, int cf_stride, int need_ldp, int need_ltq,
-                        int want_base, size_t smem, cudaStream_t stream) {
-  auto kern = hl_post_physics_fused_kernel<CPU_MATH, NIT, NBIT>;
+template <bool CPU_MATH, int NIT, int NBIT, bool HCLIP>
+static int launch_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, const FusedArgs& fa, size_t smem,
+                        cudaStream_t stream) {
+  auto kern = hl_post_physics_fused_kernel<CPU_MATH, NIT, NBIT, HCLIP>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1130,7 +1156,7 @@ static int launch_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, i
     attr_set = true;
   }
   const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
-  kern<<<blocks, FUSED_THREADS, smem, stream>>>(*cfg, *bufs, n, cf_stride, need_ldp, need_ltq, want_base);
+  kern<<<blocks, FUSED_THREADS, smem, stream>>>(*cfg, *bufs, n, fa);
   return HL_OK;
 }
 
@@ -1146,6 +1172,12 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
                "null buffer");
   HL_CHECK_ARG(cfg->mesh_type == 0 || b.height_min3, "the fused step needs the min3 terrain table (hl_terrain_prepare)");
   HL_CHECK_ARG(cfg->measure_heights, "the fused step needs measure_heights (privileged obs carries the scan)");
+  {
+    const void* al[] = {b.root_states, b.dof_state, b.contact_forces, b.actions, b.last_actions, b.last_last_actions,
+                        b.last_dof_pos, b.last_dof_vel, b.torques, b.last_torques, b.last_root_vel, b.commands,
+                        b.feet_air_time, b.last_contacts, b.contact_filt};
+    for (const void* q : al) HL_CHECK_ARG(((uintptr_t)q & 15) == 0, "state tensors must be 16-byte aligned");
+  }
   if (n <= 0) return HL_OK;
   int cf_stride = cfg->num_bodies * 3;
   if ((cf_stride & 1) == 0) cf_stride += 1;
@@ -1161,14 +1193,31 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
   const int P = cfg->n_px * cfg->n_py, PB = cfg->n_bx * cfg->n_by;
   const bool cpu = cfg->index_math == HL_INDEX_MATH_TORCH_CPU;
   const cudaStream_t st = (cudaStream_t)stream;
-  int rc;
-  if (P <= 192 && PB <= 64) {
-    rc = cpu ? launch_fused<true, 6, 2>(cfg, bufs, n, cf_stride, need_ldp, need_ltq, want_base, smem, st)
-             : launch_fused<false, 6, 2>(cfg, bufs, n, cf_stride, need_ldp, need_ltq, want_base, smem, st);
-  } else {
-    rc = cpu ? launch_fused<true, 8, 8>(cfg, bufs, n, cf_stride, need_ldp, need_ltq, want_base, smem, st)
-             : launch_fused<false, 8, 8>(cfg, bufs, n, cf_stride, need_ldp, need_ltq, want_base, smem, st);
+  // |height obs| <= obs_height + noise: the +-clip_obs clip of step() is compiled out when it cannot bind
+  const bool hclip = (cfg->obs_height + (cfg->add_noise ? cfg->noise_height : 0.0f)) > cfg->clip_obs;
+  FusedArgs fa;
+  fa.cf_stride = cf_stride;
+  fa.need_ldp = need_ldp;
+  fa.need_ltq = need_ltq;
+  fa.want_base = want_base;
+  fa.hist_clipped = (int)(b.flags & HL_BUF_HISTORY_CLIPPED);
+  {
+    uint32_t x = (uint32_t)b.philox_seed, y = (uint32_t)(b.philox_seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+      fa.keys.kx[r] = x;
+      fa.keys.ky[r] = y;
+      x += 0x9E3779B9u;
+      y += 0xBB67AE85u;
+    }
   }
+  int rc;
+#define HL_LAUNCH(CPU, NI, NB, HC) launch_fused<CPU, NI, NB, HC>(cfg, bufs, n, fa, smem, st)
+  if (P > 160 && P <= 192 && PB <= 64 && !hclip) {
+    rc = cpu ? HL_LAUNCH(true, 6, 2, false) : HL_LAUNCH(false, 6, 2, false);
+  } else {
+    rc = cpu ? HL_LAUNCH(true, 8, 8, true) : HL_LAUNCH(false, 8, 8, true);
+  }
+#undef HL_LAUNCH
   if (rc) return rc;
   HL_CHECK_LAUNCH();
   return HL_OK;

@@ -269,8 +269,10 @@ class FusedLeggedRobot:
     # ------------------------------------------------------------------ fused step pieces
     def fused_pre_reset(self):
         """Launch the fused kernel, the id compaction and the terminal rows; no host sync."""
-        c, b = ctypes.byref(self._c), ctypes.byref(self._buffers())
+        bufs = self._buffers()
+        c, b = ctypes.byref(self._c), ctypes.byref(bufs)
         L.check(L.lib.hl_post_physics_fused(c, b, self.num_envs, L.stream()))
+        bufs.flags |= 1          # HL_BUF_HISTORY_CLIPPED: the step just clipped the whole obs_buf (LR:168)
         L.check(L.lib.hl_select_reset_ids(L.ptr(self.reset_buf), self.num_envs, L.ptr(self._reset_ids),
                                           L.ptr(self._n_reset), L.ptr(self._select_ws), L.stream()))
         self._terminal_rows(self._reset_ids, self._n_reset)
