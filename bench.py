@@ -169,23 +169,23 @@ class Workload:
         self.launches = 0
 
     def env_step(self, time_fused=False):
-        import ctypes
-        from isaacgymloco_b200 import _lib as L
         env = self.env
         for k in range(env.cfg.decimation):
             env._compute_torques_into(env.delayed_actions[:, k], env.torques)
-        c, b = ctypes.byref(env._c), ctypes.byref(env._buffers())
         if time_fused:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        L.check(L.lib.hl_post_physics_fused(c, b, env.num_envs, L.stream()))
-        if time_fused:
-            e1.record()
-            self.fused_ms.append((e0, e1))
-        L.check(L.lib.hl_select_reset_ids(L.ptr(env.reset_buf), env.num_envs, L.ptr(env._reset_ids), L.ptr(env._n_reset),
-                                          L.ptr(env._select_ws), L.stream()))
-        env._terminal_rows(env._reset_ids, env._n_reset)
-        env.fused_post_reset(with_reset_zero=True)   # no torch reset_idx in the replay loop
+            def hook():
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+
+                def after():
+                    e1.record()
+                    self.fused_ms.append((e0, e1))
+                return after
+            env._fused_event_hook = hook
+        else:
+            env._fused_event_hook = None
+        env.fused_pre_reset()                          # fused kernel, reset-id compaction, terminal rows
+        env.fused_post_reset(with_reset_zero=True)     # no torch reset_idx in the replay loop
         env.common_step_counter += 1
         self.launches += env.cfg.decimation + 4
 

@@ -120,6 +120,7 @@ class FusedLeggedRobot:
         self._philox_seed = int(seed)
         self._c = cfg.to_c()
         self._bufs = None
+        self._fused_event_hook = None      # bench.py: CUDA-event pair around the fused kernel
         self._prepare_terrain()
 
     # ------------------------------------------------------------------ plumbing
@@ -271,7 +272,10 @@ class FusedLeggedRobot:
         """Launch the fused kernel, the id compaction and the terminal rows; no host sync."""
         bufs = self._buffers()
         c, b = ctypes.byref(self._c), ctypes.byref(bufs)
+        ev = self._fused_event_hook() if self._fused_event_hook is not None else None
         L.check(L.lib.hl_post_physics_fused(c, b, self.num_envs, L.stream()))
+        if ev is not None:
+            ev()
         bufs.flags |= 1          # HL_BUF_HISTORY_CLIPPED: the step just clipped the whole obs_buf (LR:168)
         L.check(L.lib.hl_select_reset_ids(L.ptr(self.reset_buf), self.num_envs, L.ptr(self._reset_ids),
                                           L.ptr(self._n_reset), L.ptr(self._select_ws), L.stream()))
