@@ -26,10 +26,6 @@ from . import _lib as L
 from .config import HotPathCfg
 
 
-class _ObsScales:
-    pass
-
-
 class FusedLeggedRobot:
     """Standalone env shard over replayed/synthetic PhysX tensors.  All tensors live on `device`
     (a CUDA device) and carry the reference's attribute names."""
@@ -71,24 +67,45 @@ class FusedLeggedRobot:
         self.episode_length_buf = state["episode_length_buf"].to(dev, torch.long).contiguous()
         self.terrain_levels = state["terrain_levels"].to(dev, torch.long).contiguous()
         self.last_contacts = state["last_contacts"].to(dev, torch.bool).contiguous()
-        self.contact_filt = torch.zeros(n, 4, dtype=torch.bool, device=dev)
         self.base_lin_vel = f32("base_lin_vel")
         self.base_ang_vel = f32("base_ang_vel")
         self.projected_gravity = f32("projected_gravity")
-        self.feet_pos = torch.zeros(n, 4, 3, device=dev)
-        self.feet_vel = torch.zeros(n, 4, 3, device=dev)
         self.rew_buf = torch.zeros(n, device=dev)
         self.reset_buf = torch.ones(n, dtype=torch.bool, device=dev)
         self.time_out_buf = torch.zeros(n, dtype=torch.bool, device=dev)
-        self.measured_heights = torch.zeros(n, self.num_height_points, device=dev)
-        self.joint_pos_target = torch.zeros(n, 12, device=dev)
+        self.height_samples = height_samples.to(dev, torch.int16).contiguous()
+        self._initial_episode_sums = state.get("episode_sums")
+        self._hl_attach(cfg, seed=seed)
+
+    def _hl_attach(self, cfg: HotPathCfg, seed: int = 0):
+        """Everything the kernels need on top of the reference's own buffers (LR:913-1032).  Also the
+        hook for mixing this class into the reference's LeggedRobot: call it at
+        the end of `_init_buffers` once the PhysX tensors are wrapped."""
+        self.cfg_hot = cfg
+        if not hasattr(self, "cfg") or self.cfg is None:
+            self.cfg = cfg
+        dev = self.device = torch.device(self.device)
+        n = self.num_envs
+        self.num_height_points = len(cfg.measured_points_x) * len(cfg.measured_points_y)
+        self.num_one_step_privileged_obs = 51 + (self.num_height_points if cfg.measure_heights else 0)
+        for name, shape, dt in (("contact_filt", (n, 4), torch.bool), ("feet_pos", (n, 4, 3), torch.float32),
+                                ("feet_vel", (n, 4, 3), torch.float32),
+                                ("measured_heights", (n, self.num_height_points), torch.float32),
+                                ("joint_pos_target", (n, 12), torch.float32),
+                                ("delayed_actions", (n, cfg.decimation, 12), torch.float32)):
+            cur = getattr(self, name, None)
+            if not (isinstance(cur, torch.Tensor) and tuple(cur.shape) == shape and cur.dtype == dt
+                    and cur.is_contiguous() and cur.device == dev):
+                setattr(self, name, torch.zeros(*shape, dtype=dt, device=dev))
+        if self.reset_buf.dtype != torch.bool:                 # base_task.py:72 starts it as int64 ones
+            self.reset_buf = self.reset_buf.to(torch.bool)
         self._base_heights = torch.zeros(n, device=dev)
-        self.delayed_actions = torch.zeros(n, cfg.decimation, 12, device=dev)
         # episode sums: one (R,N) buffer; the dict holds row views so reference code keeps working
         names = cfg.episode_sum_names()
         self._episode_sums_buf = torch.zeros(max(len(names), 1), n, device=dev)
-        if "episode_sums" in state and len(names):
-            self._episode_sums_buf[:len(names)].copy_(state["episode_sums"][:len(names)].to(dev))
+        init = getattr(self, "_initial_episode_sums", None)
+        if init is not None and len(names):
+            self._episode_sums_buf[:len(names)].copy_(init[:len(names)].to(dev))
         self.episode_sums = {nm: self._episode_sums_buf[k] for k, nm in enumerate(names)}
         self.reward_names, scales = cfg.active_terms()
         self.reward_scales = dict(zip(self.reward_names, scales))
@@ -106,8 +123,7 @@ class FusedLeggedRobot:
         self.feet_indices = torch.tensor(cfg.feet_indices, dtype=torch.long, device=dev)
         self.penalised_contact_indices = torch.tensor(cfg.penalised_contact_indices, dtype=torch.long, device=dev)
         self.termination_contact_indices = torch.tensor(cfg.termination_contact_indices, dtype=torch.long, device=dev)
-        # terrain: int16 table + the one-off min-of-3 table
-        self.height_samples = height_samples.to(dev, torch.int16).contiguous()
+        # terrain: the one-off min-of-3 table
         self._height_min3 = None
         # reset-id compaction + terminal rows (capacity N; counts live on the device)
         self._reset_ids = torch.zeros(n, dtype=torch.long, device=dev)
@@ -125,11 +141,11 @@ class FusedLeggedRobot:
 
     # ------------------------------------------------------------------ plumbing
     def _prepare_terrain(self):
-        if self.cfg.is_plane:
+        if self.cfg_hot.is_plane:
             return
         rows, cols = self.height_samples.shape
-        if (rows, cols) != tuple(self.cfg.terrain_shape):
-            raise ValueError(f"height_samples is {rows}x{cols}, cfg expects {self.cfg.terrain_shape}")
+        if (rows, cols) != tuple(self.cfg_hot.terrain_shape):
+            raise ValueError(f"height_samples is {rows}x{cols}, cfg expects {self.cfg_hot.terrain_shape}")
         self._height_min3 = torch.empty(rows - 1, cols - 1, dtype=torch.int16, device=self.device)
         L.check(L.lib.hl_terrain_prepare(L.ptr(self.height_samples), rows, cols, L.ptr(self._height_min3), L.stream()))
 
@@ -301,10 +317,10 @@ class FusedLeggedRobot:
 
     def step(self, actions):
         """LR:122-176 (7-tuple; the AMP runner reads terminal_amp_states off `extras`)."""
-        clip = self.cfg.clip_actions
+        clip = self.cfg_hot.clip_actions
         torch.clamp(actions.to(self.device), -clip, clip, out=self.actions)
         self._delay_actions()
-        for k in range(self.cfg.decimation):
+        for k in range(self.cfg_hot.decimation):
             self._compute_torques_into(self.delayed_actions[:, k], self.torques)
             if self.physics_step_fn is not None:
                 self.physics_step_fn(self, k)
@@ -315,7 +331,7 @@ class FusedLeggedRobot:
     # ------------------------------------------------------------------ torch-side hooks (RNG / PhysX; out of scope)
     def _delay_actions(self):
         """LR:133-138 (torch RNG draw of the per-env action delay)."""
-        dec = self.cfg.decimation
+        dec = self.cfg_hot.decimation
         delay = torch.randint(0, dec, (self.num_envs, 1), device=self.device)
         steps = torch.arange(dec, device=self.device).view(1, dec, 1)
         mask = (steps >= delay.view(-1, 1, 1)).to(self.actions.dtype)
