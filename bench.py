@@ -170,7 +170,7 @@ class Workload:
 
     def env_step(self, time_fused=False):
         env = self.env
-        for k in range(env.cfg.decimation):
+        for k in range(env.cfg_hot.decimation):
             env._compute_torques_into(env.delayed_actions[:, k], env.torques)
         if time_fused:
             def hook():
@@ -187,7 +187,7 @@ class Workload:
         env.fused_pre_reset()                          # fused kernel, reset-id compaction, terminal rows
         env.fused_post_reset(with_reset_zero=True)     # no torch reset_idx in the replay loop
         env.common_step_counter += 1
-        self.launches += env.cfg.decimation + 4
+        self.launches += env.cfg_hot.decimation + (2 if env.single_launch else 3)
 
     def rollout(self, time_fused=False):
         for _ in range(self.t_len):
@@ -337,7 +337,7 @@ def measure_e2e(wl, args, world):
         for k in names_in:
             dev_in[k].view(-1).copy_(host_in[k].view(-1), non_blocking=True)
         env._delay_actions()
-        for k in range(env.cfg.decimation):
+        for k in range(env.cfg_hot.decimation):
             env._compute_torques_into(env.delayed_actions[:, k], env.torques)
         env.post_physics_step()                      # public API (includes the reference's host sync on the reset count)
         for k, v in outs.items():

@@ -157,6 +157,16 @@ typedef struct HlEnvBuffers {
   uint64_t philox_offset;         /* advance by 1 per step */
   int32_t* height_idx_out;        /* optional debug: (N,n_px*n_py,2) clipped (px,py) */
   float* base_height_out;         /* (N,) written by HL_ST_BASE_HEIGHT */
+  /* Optional single-launch mode of hl_post_physics_fused: when reset_ids_out is non-NULL the fused
+   * kernel itself emits what hl_select_reset_ids + hl_terminal_rows would (ascending ids by a
+   * decoupled look-back over the CTAs; terminal rows from the data the CTA already holds). */
+  int64_t* reset_ids_out;         /* (N,) capacity */
+  int32_t* n_reset_out;           /* (1,) */
+  float* term_priv_out;           /* (N, 51+P) capacity: compute_termination_observations rows */
+  float* term_amp_out;            /* (N, 30) capacity or NULL */
+  const float* term_noise_u45;    /* pre-drawn U[0,1) for the terminal rows, or NULL => Philox stream 1 */
+  const float* term_noise_u187;
+  uint64_t* fused_ws;             /* hl_fused_workspace_bytes(N) bytes, zeroed ONCE at allocation */
 } HlEnvBuffers;
 
 int hl_version(void);
@@ -182,6 +192,7 @@ int hl_terrain_prepare(const int16_t* height_samples, int32_t rows, int32_t cols
  * of step() LR:167-171).  Observations are written speculatively for every env; envs that reset
  * are patched afterwards by hl_post_reset_fixup. */
 int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n_envs, void* stream);
+int64_t hl_fused_workspace_bytes(int64_t n_envs);
 
 /* Any subset of stages, for the individual drop-in methods (check_termination(),
  * compute_reward(), compute_observations(), _get_heights(), ...).  If `env_ids` is non-NULL the
@@ -203,6 +214,15 @@ int hl_terminal_rows(const HlCfg* cfg, const HlEnvBuffers* bufs, const int64_t* 
                      const int32_t* n_ids_dev, const float* term_noise_u45,
                      const float* term_noise_u187, float* term_priv_obs_out /* (cap,238) */,
                      float* term_amp_out /* (cap,30) or NULL */, int64_t n_envs, void* stream);
+
+/* hl_select_reset_ids + hl_terminal_rows in ONE multi-CTA launch (ordered by summing the counts of
+ * the lower-numbered CTAs).  workspace: hl_select_terminal_workspace_bytes(n) bytes, zeroed ONCE at
+ * allocation (the kernel re-arms it itself: CUDA-graph safe).  out_priv may be NULL (ids only). */
+int64_t hl_select_terminal_workspace_bytes(int64_t n_envs);
+int hl_select_and_terminal(const HlCfg* cfg, const HlEnvBuffers* bufs, const float* term_noise_u45,
+                           const float* term_noise_u187, int64_t* ids_out, int32_t* count_out,
+                           float* term_priv_obs_out, float* term_amp_out, void* workspace, int64_t n_envs,
+                           void* stream);
 
 /* After reset_idx mutated the reset envs: re-scan their heights (LR:332-333), rewrite slot 0 of
  * obs_buf and privileged_obs_buf from the post-reset state (stale base velocities, LR:232) and

@@ -27,7 +27,8 @@ class HlEnvBuffers(ctypes.Structure):
         "feet_vel", "reset_buf", "time_out_buf", "rew_buf", "obs_buf_in", "obs_buf_out",
         "privileged_obs_buf", "noise_u45", "noise_u187")] + [
         ("philox_seed", c_uint64), ("philox_offset", c_uint64), ("height_idx_out", _vp),
-        ("base_height_out", _vp)]
+        ("base_height_out", _vp), ("reset_ids_out", _vp), ("n_reset_out", _vp), ("term_priv_out", _vp),
+        ("term_amp_out", _vp), ("term_noise_u45", _vp), ("term_noise_u187", _vp), ("fused_ws", _vp)]
 
 
 # stage bits (include/himloco_b200.h)
@@ -43,10 +44,13 @@ EXPORTS = {
     "hl_pd_torque": (c_int32, [POINTER(HlCfg), _vp, c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
     "hl_terrain_prepare": (c_int32, [_vp, c_int32, c_int32, _vp, _vp]),
     "hl_post_physics_fused": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), c_int64, _vp]),
+    "hl_fused_workspace_bytes": (c_int64, [c_int64]),
     "hl_post_physics_stages": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), c_uint32, _vp, _vp, c_int64, _vp]),
     "hl_select_workspace_bytes": (c_int64, [c_int64]),
     "hl_select_reset_ids": (c_int32, [_vp, c_int64, _vp, _vp, _vp, _vp]),
     "hl_terminal_rows": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), _vp, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
+    "hl_select_terminal_workspace_bytes": (c_int64, [c_int64]),
+    "hl_select_and_terminal": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
     "hl_post_reset_fixup": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), _vp, _vp, c_int32, c_int64, _vp]),
     "hl_amp_observations": (c_int32, [_vp, _vp, _vp, _vp, c_int64, _vp]),
     "hl_gae_scan": (c_int32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, c_int32, c_int64, c_float, c_float, _vp]),

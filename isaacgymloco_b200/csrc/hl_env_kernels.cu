@@ -277,9 +277,11 @@ __device__ __forceinline__ int hl_priv_dim(const HlCfg& c) { return 51 + (c.meas
 // One warp per env (optionally per listed env id); scalars are computed redundantly by all lanes,
 // vector work (scan, obs rows) is lane-parallel.  Serves the individual drop-in methods and the
 // post-reset fix-up; the hot path is hl_post_physics_fused_kernel below.
-__global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, unsigned stages,
+template <unsigned STAGES>  // 0 = take the mask at run time; otherwise everything else is compiled out
+__global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, unsigned stages_rt,
                                                        const long long* __restrict__ ids,
                                                        const int* __restrict__ n_ids, long long n) {
+  const unsigned stages = STAGES ? STAGES : stages_rt;
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -498,7 +500,14 @@ static int launch_stage(const HlCfg* cfg, const HlEnvBuffers* bufs, unsigned sta
   if (n <= 0) return HL_OK;
   long long blocks = (n * 32 + 255) / 256;
   if (ids) blocks = blocks < 148 * 8 ? blocks : 148 * 8;  // id lists are short; grid-stride covers the rest
-  hl_stage_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*cfg, *bufs, stages, (const long long*)ids, n_ids, n);
+  constexpr unsigned FIX = HL_ST_HEIGHTS | HL_ST_OBS | HL_ST_OBS_NOSHIFT | HL_ST_OBS_CLIP | HL_ST_ROLL;
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (stages == FIX)
+    hl_stage_kernel<FIX><<<(unsigned)blocks, 256, 0, st>>>(*cfg, *bufs, stages, (const long long*)ids, n_ids, n);
+  else if (stages == (FIX | HL_ST_RESET_ZERO))
+    hl_stage_kernel<FIX | HL_ST_RESET_ZERO><<<(unsigned)blocks, 256, 0, st>>>(*cfg, *bufs, stages, (const long long*)ids, n_ids, n);
+  else
+    hl_stage_kernel<0u><<<(unsigned)blocks, 256, 0, st>>>(*cfg, *bufs, stages, (const long long*)ids, n_ids, n);
   HL_CHECK_LAUNCH();
   return HL_OK;
 }
@@ -593,6 +602,160 @@ extern "C" int hl_terminal_rows(const HlCfg* cfg, const HlEnvBuffers* bufs, cons
   if (n <= 0) return HL_OK;
   hl_terminal_rows_kernel<<<(unsigned)((n * 32 + 255) / 256 < 148 * 8 ? (n * 32 + 255) / 256 : 148 * 8), 256, 0, (cudaStream_t)stream>>>(*cfg, *bufs, (const long long*)env_ids, n_ids_dev, u45,
                                                                  u187, out_priv, out_amp, n);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}
+
+// ============================================================================= ids + terminal rows
+// One launch for LR:225-228: env_ids = reset_buf.nonzero().flatten(), then
+// compute_termination_observations(env_ids) and get_amp_observations()[env_ids].
+// CTA = 1024 consecutive envs: flags -> block scan -> (sum of the counts of all lower CTAs, which
+// were dispatched earlier and publish right after their scan) -> ordered ids -> the CTA's warps
+// write the rows of its own reset envs.  ws = {pad, done, epoch, pad, state[nblocks]}.
+constexpr int SEL_ENVS = 256;   // small tiles: the rows of a CTA's ~6 reset envs go one per warp
+__global__ void __launch_bounds__(256) hl_select_terminal_kernel(HlCfg c, HlEnvBuffers b, const float* __restrict__ u45,
+                                                                 const float* __restrict__ u187,
+                                                                 long long* __restrict__ ids_out, int* __restrict__ count_out,
+                                                                 float* __restrict__ out_priv, float* __restrict__ out_amp,
+                                                                 unsigned long long* ws, long long n) {
+  __shared__ int warp_tot[8];
+  __shared__ int s_excl, s_total;
+  __shared__ unsigned s_epoch;
+  __shared__ int s_local[SEL_ENVS];  // local env offsets of this CTA's reset envs, ascending
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned vb = blockIdx.x, nblocks = gridDim.x;
+  unsigned* ctrl = reinterpret_cast<unsigned*>(ws);
+  volatile unsigned long long* state = reinterpret_cast<volatile unsigned long long*>(ws) + 2;
+  if (tid == 0) s_epoch = *reinterpret_cast<volatile unsigned*>(ctrl + 2) + 1u;
+  const long long e0 = (long long)vb * SEL_ENVS;
+  // one flag per thread
+  const long long off = e0 + tid;
+  const unsigned mask = (off < n && b.reset_buf[off]) ? 1u : 0u;
+  const int cnt = (int)mask;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  int wbase = 0;
+  for (int w = 0; w < wid; ++w) wbase += warp_tot[w];
+  if (tid == 0) {
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) tot += warp_tot[w];
+    s_total = tot;
+    state[vb] = ((unsigned long long)s_epoch << 32) | (unsigned)tot;  // publish early
+    __threadfence();
+  }
+  int pos = wbase + incl - cnt;
+  if (mask) s_local[pos] = tid;
+  __syncthreads();
+  if (wid == 0) {  // exclusive prefix = sum of the counts of all lower CTAs
+    const unsigned ep = s_epoch;
+    int acc = 0;
+    for (unsigned base = 0; base < vb; base += 32 * 8) {
+      unsigned long long w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const unsigned j = base + u * 32 + lane;
+        w[u] = j < vb ? state[j] : ((unsigned long long)ep << 32);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const unsigned j = base + u * 32 + lane;
+        while ((unsigned)(w[u] >> 32) != ep) w[u] = state[j];
+        acc += (int)(unsigned)w[u];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      s_excl = acc;
+      if (vb == nblocks - 1) *count_out = acc + s_total;
+    }
+  }
+  __syncthreads();
+  const int excl = s_excl, total = s_total;
+  for (int i = tid; i < total; i += 256) ids_out[excl + i] = e0 + s_local[i];
+  // rows: one warp per reset env of this CTA
+  const int B = c.num_bodies, P = c.n_px * c.n_py, PD = hl_priv_dim(c);
+  if (out_priv) {
+    int cb, c0;
+    hl_cur_noise_slot(P, cb, c0);
+    for (int i = wid; i < total; i += 8) {
+      const long long e = e0 + s_local[i], r = excl + i;
+      EnvView v;
+      v.root = b.root_states + e * 13;
+      v.dof = b.dof_state + e * 24;
+      v.act = b.actions + e * 12;
+      EnvScalars s;
+      s.gid = e + c.env_id_offset;
+      for (int k = 0; k < 4; ++k) s.cmd[k] = b.commands[e * 4 + k];
+      for (int k = 0; k < 3; ++k) {
+        s.blv[k] = b.base_lin_vel[e * 3 + k];
+        s.bav[k] = b.base_ang_vel[e * 3 + k];
+        s.pg[k] = b.projected_gravity[e * 3 + k];
+      }
+      uint4 nb = make_uint4(0u, 0u, 0u, 0u);
+      if (c.add_noise && !u45) nb = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)s.gid, (unsigned)(cb * 32 + lane), 1u);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        if (k < 45) {
+          float u = 0.5f;
+          if (c.add_noise) u = u45 ? u45[e * 45 + k] : hl_u01(hl_pick(nb, c0 + h));
+          out_priv[r * PD + k] = hl_add_noise45(c, hl_obs45(c, v, s, k), u, k);
+        }
+      }
+      if (lane < 6) out_priv[r * PD + 45 + lane] = lane < 3 ? s.blv[lane] * c.obs_lin_vel : b.disturbance[e * B * 3 + (lane - 3)];
+      if (c.measure_heights) {
+        HeightNoise hn;
+        const float rz = v.root[2];
+        float mh[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) mh[it] = (it * 32 + lane < P) ? b.measured_heights[e * P + it * 32 + lane] : 0.0f;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (it * 32 >= P) break;
+          const int p = it * 32 + lane;
+          if (!u187 && (it & 3) == 0) hn.refill(b, (unsigned long long)s.gid, it >> 2, lane, 1u);
+          float u = 0.5f;
+          if (c.add_noise) u = u187 ? (p < P ? u187[e * P + p] : 0.5f) : hn.get(it, lane);
+          if (p < P) out_priv[r * PD + 51 + p] = hl_obs_height(c, rz, mh[it], u);
+        }
+      }
+      if (out_amp && lane < 30) {
+        float x;
+        if (lane < 12) x = v.dof_pos(lane);
+        else if (lane < 15) x = s.blv[lane - 12];
+        else if (lane < 18) x = s.bav[lane - 15];
+        else x = v.dof_vel(lane - 18);
+        out_amp[r * 30 + lane] = x;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {  // last CTA re-arms the workspace (graph safe)
+    __threadfence();
+    if (atomicAdd(ctrl + 1, 1u) == nblocks - 1) {
+      ctrl[1] = 0u;
+      ctrl[2] = s_epoch;
+      __threadfence();
+    }
+  }
+}
+
+extern "C" int64_t hl_select_terminal_workspace_bytes(int64_t n) { return (int64_t)(((n + SEL_ENVS - 1) / SEL_ENVS) + 2) * 8; }
+extern "C" int hl_select_and_terminal(const HlCfg* cfg, const HlEnvBuffers* bufs, const float* u45, const float* u187,
+                                      int64_t* ids_out, int32_t* count_out, float* out_priv, float* out_amp,
+                                      void* workspace, int64_t n, void* stream) {
+  if (int r = check_cfg(cfg, bufs)) return r;
+  HL_CHECK_ARG(ids_out && count_out && workspace && bufs->reset_buf, "null pointer");
+  if (n <= 0) return HL_OK;
+  hl_select_terminal_kernel<<<(unsigned)((n + SEL_ENVS - 1) / SEL_ENVS), 256, 0, (cudaStream_t)stream>>>(
+      *cfg, *bufs, u45, u187, (long long*)ids_out, count_out, out_priv, out_amp, (unsigned long long*)workspace, n);
   HL_CHECK_LAUNCH();
   return HL_OK;
 }
@@ -705,11 +868,18 @@ extern "C" int hl_select_reset_ids(const uint8_t* reset_buf, int64_t n, int64_t*
 //   phase 2  coalesced stores: obs history shift (register-staged, in-place safe), slot 0,
 //            privileged_obs[0:51], the last_* roll (skipped for envs that reset: the post-reset
 //            fix-up redoes it after reset_idx).
-constexpr int EPB = 64;
+#ifndef HL_EPB
+#define HL_EPB 32
+#endif
+#ifndef HL_SCALAR_WARPS
+#define HL_SCALAR_WARPS 1
+#endif
+constexpr int EPB = HL_EPB;
 constexpr int FUSED_THREADS = 256;
-constexpr int SCALAR_WARPS = 2;
+constexpr int SCALAR_WARPS = HL_SCALAR_WARPS;
+static_assert(SCALAR_WARPS * 32 >= EPB && EPB % 4 == 0 && EPB <= 64, "one lane per env; 16-B aligned slabs");
 constexpr int SCAN_WARPS = FUSED_THREADS / 32 - SCALAR_WARPS;
-constexpr int S13 = 13, SDOF = 25, SFOOT = 25, SCUR = 51;
+constexpr int S13 = 13, SDOF = 25, SFOOT = 25, SCUR = 57;
 constexpr int ENVS_PER_SCAN_WARP = (EPB + SCAN_WARPS - 1) / SCAN_WARPS;
 
 struct FusedSmem {
@@ -720,6 +890,8 @@ struct FusedSmem {
   float cur[EPB * SCUR];
   float base_h[EPB];
   unsigned char reset[EPB];
+  int cnt_reset, arrive, excl;  // single-launch compaction: resets in this CTA, scalar-warp arrivals, exclusive prefix
+  unsigned vb, epoch;           // virtual block id (ticket order) and look-back epoch
   // dynamic tail: contact forces (EPB*cf_stride), then optional last_dof_pos / last_torques slabs
 };
 
@@ -772,18 +944,27 @@ __device__ __forceinline__ int scan_gather(const HlCfg& c, const int16_t* __rest
   const float ry = __fadd_rn(__fadd_rn(by, ay), cy);
   const int ix = cell32<CPU_MATH>(__fadd_rn(rx, posx), c.border_size, c.horizontal_scale, c.inv_horizontal_scale, c.terrain_rows - 2);
   const int iy = cell32<CPU_MATH>(__fadd_rn(ry, posy), c.border_size, c.horizontal_scale, c.inv_horizontal_scale, c.terrain_cols - 2);
+#ifdef HL_EXP_NO_GATHER
+  return ix + iy;
+#else
   return (int)__ldg(min3 + (unsigned)(ix * pitch + iy));
+#endif
 }
 
 struct FusedArgs {
   int cf_stride, need_ldp, need_ltq, want_base;
+  int compact;            // emit reset ids / count / terminal rows from this launch (decoupled look-back)
   int hist_clipped;       // obs history is known to be within +-clip_obs already (every step after the first)
   HlPhiloxKeys keys;      // Philox round keys of bufs.philox_seed (host-computed: constant-bank operands)
 };
 
 template <bool CPU_MATH, int NIT, int NBIT, bool HCLIP>
 __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel(HlCfg c, HlEnvBuffers b, long long n, FusedArgs fa) {
+#ifdef HL_EXP_NO_BASE
+  const int cf_stride = fa.cf_stride, need_ldp = fa.need_ldp, need_ltq = fa.need_ltq, want_base = 0;
+#else
   const int cf_stride = fa.cf_stride, need_ldp = fa.need_ldp, need_ltq = fa.need_ltq, want_base = fa.want_base;
+#endif
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
   float* s_cf = reinterpret_cast<float*>(smem_raw + sizeof(FusedSmem));
@@ -791,7 +972,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
   float* s_ltq = s_ldp + (need_ldp ? EPB * S13 : 0);
   float* s_sums = s_ltq + (need_ltq ? EPB * S13 : 0);  // (R, EPB) episode sums of this block
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const long long e0 = (long long)blockIdx.x * EPB;
+  // Single-launch compaction: every CTA publishes its reset count early (right after
+  // termination); at its end it sums the counts of all lower-numbered CTAs.  A CTA only waits on
+  // CTAs with a smaller blockIdx, which the hardware dispatched before it, so they are running
+  // or done: no deadlock.  ws = {unused, done, epoch, pad, state[nblocks]}, state = epoch<<32 | count.
+  unsigned* ctrl = reinterpret_cast<unsigned*>(b.fused_ws);
+  volatile unsigned long long* lb_state = reinterpret_cast<volatile unsigned long long*>(b.fused_ws) + 2;
+  const unsigned vb = blockIdx.x;
+  if (fa.compact && tid == 0) {
+    sm.epoch = *reinterpret_cast<volatile unsigned*>(ctrl + 2) + 1u;   // visible after the phase-0 barrier
+    sm.cnt_reset = 0;
+    sm.arrive = 0;
+  }
+  const long long e0 = (long long)vb * EPB;
   const int cnt = (int)((n - e0) < EPB ? (n - e0) : EPB);
   const int B = c.num_bodies, P = c.n_px * c.n_py, PD = 51 + P;
 
@@ -810,16 +1003,20 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
     const int n_root = (cnt * 13) >> 2, n_dof = (cnt * 24) >> 2, n_cf = (cnt * B * 3) >> 2, n_a = (cnt * 12) >> 2;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 r_root = tid < n_root ? __ldg(root4 + tid) : z4;
-    float4 r_dof[2], r_cf[4], r_a[5];
+    constexpr int NJ_DOF = (EPB * 6 + FUSED_THREADS - 1) / FUSED_THREADS;        // float4s per thread
+    constexpr int NJ_CF = (EPB * 51 / 4 + FUSED_THREADS - 1) / FUSED_THREADS;    // sized for 17 bodies; more -> leftover loop
+    constexpr int NJ_FOOT = (EPB * 24 + FUSED_THREADS - 1) / FUSED_THREADS;
+    static_assert(EPB * 3 <= FUSED_THREADS && EPB * 13 / 4 < FUSED_THREADS, "one float4 per thread for the 12/13-wide slabs");
+    float4 r_dof[NJ_DOF], r_cf[NJ_CF], r_a[5];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) r_dof[j] = tid + j * FUSED_THREADS < n_dof ? __ldg(dof4 + tid + j * FUSED_THREADS) : z4;
+    for (int j = 0; j < NJ_DOF; ++j) r_dof[j] = tid + j * FUSED_THREADS < n_dof ? __ldg(dof4 + tid + j * FUSED_THREADS) : z4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) r_cf[j] = tid + j * FUSED_THREADS < n_cf ? __ldg(cf4p + tid + j * FUSED_THREADS) : z4;
+    for (int j = 0; j < NJ_CF; ++j) r_cf[j] = tid + j * FUSED_THREADS < n_cf ? __ldg(cf4p + tid + j * FUSED_THREADS) : z4;
 #pragma unroll
     for (int j = 0; j < 5; ++j) r_a[j] = tid < n_a ? __ldg(a4[j] + tid) : z4;
-    float r_foot[6];
+    float r_foot[NJ_FOOT];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {  // pos/vel of the 4 foot records only
+    for (int j = 0; j < NJ_FOOT; ++j) {  // pos/vel of the 4 foot records only
       const int i = tid + j * FUSED_THREADS;
       const int e = i / 24, r = i - e * 24, f = r / 6, k = r - f * 6;
       r_foot[j] = i < cnt * 24 ? __ldg(b.rigid_body_states + ((e0 + e) * B + c.feet_idx[f]) * 13 + (k < 3 ? k : k + 4)) : 0.f;
@@ -841,9 +1038,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
     };
     if (tid < n_root) put4(sm.root, S13, 13, tid, r_root);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) if (tid + j * FUSED_THREADS < n_dof) put4(sm.dof, SDOF, 24, tid + j * FUSED_THREADS, r_dof[j]);
+    for (int j = 0; j < NJ_DOF; ++j) if (tid + j * FUSED_THREADS < n_dof) put4(sm.dof, SDOF, 24, tid + j * FUSED_THREADS, r_dof[j]);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NJ_CF; ++j)
       if (tid + j * FUSED_THREADS < n_cf) {
         if (B == 17) put4(s_cf, 51, 51, tid + j * FUSED_THREADS, r_cf[j]);  // aliengo: constant divisor
         else put4(s_cf, cf_stride, B * 3, tid + j * FUSED_THREADS, r_cf[j]);
@@ -851,12 +1048,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
 #pragma unroll
     for (int j = 0; j < 5; ++j) if (tid < n_a) put4(a_dst[j], S13, 12, tid, r_a[j]);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
+    for (int j = 0; j < NJ_FOOT; ++j) {
       const int i = tid + j * FUSED_THREADS;
       if (i < cnt * 24) sm.foot[(i / 24) * SFOOT + (i % 24)] = r_foot[j];
     }
-    // leftovers: contact slabs beyond 4 float4 per thread (num_bodies > 21) and ragged tails
-    for (int i4 = tid + 4 * FUSED_THREADS; i4 < n_cf; i4 += FUSED_THREADS) put4(s_cf, cf_stride, B * 3, i4, __ldg(cf4p + i4));
+    // leftovers: contact slabs beyond NJ_CF float4 per thread (more bodies) and ragged tails
+    for (int i4 = tid + NJ_CF * FUSED_THREADS; i4 < n_cf; i4 += FUSED_THREADS) put4(s_cf, cf_stride, B * 3, i4, __ldg(cf4p + i4));
     for (int idx = (n_root << 2) + tid; idx < cnt * 13; idx += FUSED_THREADS) sm.root[(idx / 13) * S13 + idx % 13] = __ldg(b.root_states + e0 * 13 + idx);
     for (int idx = (n_cf << 2) + tid; idx < cnt * B * 3; idx += FUSED_THREADS)
       s_cf[(idx / (B * 3)) * cf_stride + idx % (B * 3)] = __ldg(b.contact_forces + e0 * B * 3 + idx);
@@ -915,6 +1112,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
 #pragma unroll
       for (int k = 0; k < 3; ++k) cur[45 + k] = s.blv[k] * c.obs_lin_vel;
       cur[48] = d0; cur[49] = d1; cur[50] = d2;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {  // raw velocities for the terminal AMP rows
+        cur[51 + k] = s.blv[k];
+        cur[54 + k] = s.bav[k];
+      }
     }
     __threadfence_block();
     named_bar_arrive(2, FUSED_THREADS);  // sm.cur is ready for the scan warps
@@ -925,6 +1127,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
       b.reset_buf[ge] = s.reset;
       b.time_out_buf[ge] = s.time_out;
       sm.reset[e] = s.reset;
+      if (fa.compact) {
+        const int wc = __popc(__ballot_sync(__activemask(), s.reset));
+        if (lane == 0) {
+          atomicAdd(&sm.cnt_reset, wc);
+          __threadfence_block();
+          const int live_warps = (cnt + 31) >> 5;
+          if (atomicAdd(&sm.arrive, 1) == live_warps - 1) {  // last scalar warp: publish this CTA's aggregate
+            const int tot = atomicAdd(&sm.cnt_reset, 0);
+            lb_state[vb] = ((unsigned long long)sm.epoch << 32) | (unsigned)tot;
+            __threadfence();
+          }
+        }
+      }
       if (!s.reset) {  // LR:235; reset envs: the fix-up still reads the disturbance, then zeroes it
         float* dptr = b.disturbance + ge * B * 3;
         dptr[0] = 0.0f; dptr[1] = 0.0f; dptr[2] = 0.0f;
@@ -943,7 +1158,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
     if (want_base) named_bar_sync(1, FUSED_THREADS);  // base heights are in shared memory
     if (act_lane) {
       s.base_h = sm.base_h[e];
+#ifdef HL_EXP_NO_REWARD
+      const float rew = 0.0f;
+#else
       const float rew = hl_compute_reward(c, b, v, s, b.episode_sums ? s_sums + e : nullptr, EPB, true);
+#endif
       b.rew_buf[ge] = rew;
       unsigned lc = 0;
 #pragma unroll
@@ -986,27 +1205,44 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
       if (lane < ENVS_PER_SCAN_WARP && e < cnt) hl_yaw_quat(sm.root + e * S13 + 3, qz_l, qw_l);
     }
     if (want_base) {
-      for (int li = 0, e = sw; e < cnt; e += SCAN_WARPS, ++li) {
-        const float qz = __shfl_sync(0xffffffffu, qz_l, li), qw = __shfl_sync(0xffffffffu, qw_l, li);
-        const float* root = sm.root + e * S13;
-        const float posx = root[0], posy = root[1], posz = root[2];
-        float acc = 0.0f;
-        if (!plane) {
-          int hraw[NBIT];
+      // 63-point base scans (LR:1357-1398) of all this warp's envs, batched: every gather of a batch
+      // is in flight before the first is consumed
+      constexpr int BB = ENVS_PER_SCAN_WARP < 6 ? ENVS_PER_SCAN_WARP : 6;
+      for (int l0 = 0; sw + SCAN_WARPS * l0 < cnt; l0 += BB) {
+        int hraw[BB][NBIT];
 #pragma unroll
-          for (int it = 0; it < NBIT; ++it) hraw[it] = scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, posx, posy, hx[it], hy[it]);
+        for (int q = 0; q < BB; ++q) {
+          const int e = sw + SCAN_WARPS * (l0 + q);
+          const float qz = __shfl_sync(0xffffffffu, qz_l, l0 + q), qw = __shfl_sync(0xffffffffu, qw_l, l0 + q);
+          const float* root = sm.root + (e < cnt ? e : sw) * S13;
+          const float posx = root[0], posy = root[1];
 #pragma unroll
           for (int it = 0; it < NBIT; ++it)
-            if (it * 32 + lane < PB) acc += posz - (float)hraw[it] * c.vertical_scale;
+            hraw[q][it] = (plane || e >= cnt) ? 0 : scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, posx, posy, hx[it], hy[it]);
         }
-        acc = warp_sum(acc);
-        if (lane == 0) sm.base_h[e] = plane ? posz : acc / (float)PB;
+#pragma unroll
+        for (int q = 0; q < BB; ++q) {
+          const int e = sw + SCAN_WARPS * (l0 + q);
+          if (e < cnt) {   // warp-uniform
+            const float posz = sm.root[e * S13 + 2];
+            float acc = 0.0f;
+#pragma unroll
+            for (int it = 0; it < NBIT; ++it)
+              if (it * 32 + lane < PB) acc += posz - (float)hraw[q][it] * c.vertical_scale;
+            acc = warp_sum(acc);
+            if (lane == 0) sm.base_h[e] = plane ? posz : acc / (float)PB;
+          }
+        }
       }
       __threadfence_block();
       named_bar_arrive(1, FUSED_THREADS);
     }
+#ifdef HL_EXP_NO_PHILOX
+    const bool philox = false, philox45 = false;
+#else
     const bool philox = c.add_noise && !b.noise_u187;
     const bool philox45 = c.add_noise && !b.noise_u45;
+#endif
     const float cl = c.clip_obs;
     constexpr int NPASS = (NIT + 3) / 4;
     // height obs = clamp(z - 0.5 - h, +-1) * s + (2u - 1) * nh  (LR:399-400); with u = k * 2^-24 the
@@ -1068,8 +1304,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
           else nzv = urow ? (2.0f * urow[it * 32] - 1.0f) * nh : 0.0f;
           float hv = fmaf(hl_clampf(rz05 - mh, -1.0f, 1.0f), c.obs_height, nzv);
           if (HCLIP) hv = hl_clampf(hv, -cl, cl);
+#ifndef HL_EXP_NO_HOUT
           mptr[it * 32] = mh;
           pptr[51 + it * 32] = hv;
+#else
+          if (hv == 123.456f) mptr[it * 32] = mh;
+#endif
         }
       }
       // slot 0 of obs_buf and privileged_obs[0:51]: noise, clip (LR:394,167-171)
@@ -1100,9 +1340,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
 #pragma unroll
         for (int i = 0; i < 8; ++i) old[i] = hl_clampf(old[i], -cl, cl);
       }
+#ifndef HL_EXP_NO_HIST
 #pragma unroll
       for (int i = 0; i < 7; ++i) hdst[45 + i * 32] = old[i];
       if (lane < 1) hdst[45 + 224] = old[7];
+#endif
     }
   }
   __syncthreads();
@@ -1114,7 +1356,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
       if (e < cnt) b.episode_sums[(long long)k * n + e0 + e] = s_sums[i];
     }
   // LR:235-241 for the envs that do not reset: one 128-bit store per (env, third of a row)
+#ifdef HL_EXP_NO_ROLL
+  if (tid < 0) {
+#else
   if (tid < cnt * 3) {
+#endif
     const int e = tid / 3, q = tid - e * 3;
     if (!sm.reset[e]) {
       const int so = e * S13 + q * 4;
@@ -1140,6 +1386,104 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
       if (b.feet_vel) b.feet_vel[e0 * 12 + i] = sm.foot[e * SFOOT + f * 6 + 3 + k];
     }
   }
+
+  // ---------------- phase 3 (single-launch mode): env_ids = reset_buf.nonzero() (LR:225) by a
+  // decoupled look-back over the CTAs, then compute_termination_observations / terminal AMP rows
+  // (LR:227-228) of this CTA's reset envs straight from shared memory.
+  if (fa.compact) {
+    const unsigned nblocks = gridDim.x;
+    if (wid == 0) {
+      const unsigned ep = sm.epoch;
+      int acc = 0;
+      for (unsigned base = 0; base < vb; base += 32 * 8) {  // 8 independent loads per lane in flight
+        unsigned long long w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const unsigned j = base + u * 32 + lane;
+          w[u] = j < vb ? lb_state[j] : ((unsigned long long)ep << 32);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const unsigned j = base + u * 32 + lane;
+          while ((unsigned)(w[u] >> 32) != ep) w[u] = lb_state[j];   // predecessor has not published yet
+          acc += (int)(unsigned)w[u];
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        sm.excl = acc;
+        if (vb == nblocks - 1) *b.n_reset_out = acc + sm.cnt_reset;
+      }
+    }
+    __syncthreads();
+    if (sm.cnt_reset > 0) {
+      const int excl = sm.excl;
+      int cbn, c0n;
+      hl_cur_noise_slot(P, cbn, c0n);
+      const float nh = c.add_noise ? c.noise_height : 0.0f;
+      // the reset envs of this CTA as two ballot masks; warp w takes the w-th, (w+8)-th, ... of them
+      const unsigned m0 = __ballot_sync(0xffffffffu, lane < cnt && sm.reset[lane]);
+      const unsigned m1 = __ballot_sync(0xffffffffu, lane + 32 < cnt && sm.reset[lane + 32]);
+      const int n0 = __popc(m0), ntot = n0 + __popc(m1);
+      for (int r = wid; r < ntot; r += FUSED_THREADS / 32) {
+        // env index of the r-th set bit
+        unsigned m = r < n0 ? m0 : m1;
+        int skip = r < n0 ? r : r - n0;
+        while (skip--) m &= m - 1;
+        const int e = (__ffs(m) - 1) + (r < n0 ? 0 : 32);
+        const long long ge = e0 + e, row = excl + r;
+        const unsigned long long genv = (unsigned long long)(ge + c.env_id_offset);
+        if (lane == 0) b.reset_ids_out[row] = ge;
+        const float* cur = sm.cur + e * SCUR;
+        float* out = b.term_priv_out + row * PD;
+        uint4 nb = make_uint4(0u, 0u, 0u, 0u);
+        if (c.add_noise && !b.term_noise_u45) nb = hl_noise_block(fa.keys, b.philox_offset, genv, (unsigned)(cbn * 32 + lane), 1u);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k = lane + 32 * h;
+          if (k < 51) {
+            float x = cur[k];
+            if (k < 45 && c.add_noise) {
+              const float u = b.term_noise_u45 ? b.term_noise_u45[ge * 45 + k] : hl_u01(hl_pick(nb, c0n + h));
+              x += (2.0f * u - 1.0f) * c.noise45[k];
+            }
+            out[k] = x;
+          }
+        }
+        const float rz = sm.root[e * S13 + 2];
+        uint4 hb = make_uint4(0u, 0u, 0u, 0u);
+        for (int it = 0; it * 32 < P; ++it) {
+          const int p = it * 32 + lane;
+          if (c.add_noise && !b.term_noise_u187 && (it & 3) == 0)
+            hb = hl_noise_block(fa.keys, b.philox_offset, genv, (unsigned)((it >> 2) * 32 + lane), 1u);
+          if (p < P) {
+            float u = 0.5f;
+            if (c.add_noise) u = b.term_noise_u187 ? b.term_noise_u187[ge * P + p] : hl_u01(hl_pick(hb, it & 3));
+            const float mh = b.measured_heights[ge * P + p];  // written by this CTA's scan warps
+            out[51 + p] = hl_clampf(rz - 0.5f - mh, -1.0f, 1.0f) * c.obs_height + (2.0f * u - 1.0f) * nh;
+          }
+        }
+        if (b.term_amp_out && lane < 30) {  // LR:416: dof_pos 12, base_lin_vel 3, base_ang_vel 3, dof_vel 12
+          float x;
+          if (lane < 12) x = sm.dof[e * SDOF + 2 * lane];
+          else if (lane < 18) x = cur[51 + (lane - 12)];
+          else x = sm.dof[e * SDOF + 2 * (lane - 18) + 1];
+          b.term_amp_out[row * 30 + lane] = x;
+        }
+      }
+    }
+    // the last CTA to finish re-arms the workspace for the next launch (CUDA-graph safe: no memset)
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(ctrl + 1, 1u) == nblocks - 1) {
+        ctrl[1] = 0u;
+        ctrl[2] = sm.epoch;
+        __threadfence();
+      }
+    }
+  }
 }
 
 template <bool CPU_MATH, int NIT, int NBIT, bool HCLIP>
@@ -1159,6 +1503,8 @@ static int launch_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, c
   kern<<<blocks, FUSED_THREADS, smem, stream>>>(*cfg, *bufs, n, fa);
   return HL_OK;
 }
+
+extern "C" int64_t hl_fused_workspace_bytes(int64_t n) { return (int64_t)(((n + EPB - 1) / EPB) + 2) * 8; }
 
 extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, void* stream) {
   if (int r = check_cfg(cfg, bufs)) return r;
@@ -1201,6 +1547,8 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
   fa.need_ltq = need_ltq;
   fa.want_base = want_base;
   fa.hist_clipped = (int)(b.flags & HL_BUF_HISTORY_CLIPPED);
+  fa.compact = b.reset_ids_out != nullptr;
+  HL_CHECK_ARG(!fa.compact || (b.n_reset_out && b.term_priv_out && b.fused_ws), "single-launch mode needs n_reset_out, term_priv_out, fused_ws");
   {
     uint32_t x = (uint32_t)b.philox_seed, y = (uint32_t)(b.philox_seed >> 32);
     for (int r = 0; r < 10; ++r) {

@@ -131,6 +131,11 @@ class FusedLeggedRobot:
         self._term_priv = torch.zeros(n, self.num_one_step_privileged_obs, device=dev)
         self._term_amp = torch.zeros(n, 30, device=dev)
         self._select_ws = torch.zeros(int(L.lib.hl_select_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+        self._fused_ws = torch.zeros(int(L.lib.hl_fused_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+        self._selterm_ws = torch.zeros(int(L.lib.hl_select_terminal_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+        # ids + terminal rows straight from the fused kernel: wins in the launch-bound small-N regime,
+        # costs more than the separate compaction launch at large N (measured)
+        self.single_launch = n <= 16384
         # noise: Philox by default; parity tests install pre-drawn tensors
         self._noise = {}
         self._philox_seed = int(seed)
@@ -188,6 +193,11 @@ class FusedLeggedRobot:
         b.philox_seed, b.philox_offset = self._philox_seed, self.common_step_counter
         b.height_idx_out = None
         b.base_height_out = p(self._base_heights)
+        if self.single_launch:
+            b.reset_ids_out, b.n_reset_out = p(self._reset_ids), p(self._n_reset)
+            b.term_priv_out, b.term_amp_out = p(self._term_priv), p(self._term_amp)
+            b.term_noise_u45, b.term_noise_u187 = p(self._noise.get("term45")), p(self._noise.get("term187"))
+            b.fused_ws = p(self._fused_ws)
         self._bufs = b
         return b
 
@@ -293,9 +303,11 @@ class FusedLeggedRobot:
         if ev is not None:
             ev()
         bufs.flags |= 1          # HL_BUF_HISTORY_CLIPPED: the step just clipped the whole obs_buf (LR:168)
-        L.check(L.lib.hl_select_reset_ids(L.ptr(self.reset_buf), self.num_envs, L.ptr(self._reset_ids),
-                                          L.ptr(self._n_reset), L.ptr(self._select_ws), L.stream()))
-        self._terminal_rows(self._reset_ids, self._n_reset)
+        if self.single_launch:
+            return               # ids, count and terminal rows came out of the same launch
+        L.check(L.lib.hl_select_and_terminal(c, b, L.ptr(self._noise.get("term45")), L.ptr(self._noise.get("term187")),
+                                             L.ptr(self._reset_ids), L.ptr(self._n_reset), L.ptr(self._term_priv),
+                                             L.ptr(self._term_amp), L.ptr(self._selterm_ws), self.num_envs, L.stream()))
 
     def fused_post_reset(self, with_reset_zero: bool = False):
         """Patch the reset envs after reset_idx.  with_reset_zero=True also applies reset_idx's own

@@ -239,3 +239,44 @@ def test_fixup_with_reset_zero_matches_reset_idx_bookkeeping():
         assert k > 0
         assert_equal(env._reset_ids[:k], oids, "env_ids")
         compare_snapshots(env.snapshot(), oenv.snapshot())
+
+
+def test_single_launch_equals_separate_kernels():
+    """ids / count / terminal rows emitted by the fused kernel (decoupled look-back) are identical
+    to hl_select_reset_ids + hl_terminal_rows, in Philox mode too, across several steps and for a
+    ragged env count (tail CTA)."""
+    from gpu_helpers import make_env
+    from isaacgymloco_b200 import config as C, synthetic as S
+    for n in (65536, 4096 + 37):
+        cfg = C.aliengo("stairs", num_envs=n)
+        hf = S.make_terrain(cfg, seed=2)
+        state = S.make_state(cfg, n, hf, seed=31)
+        a = make_env(cfg, state, hf)
+        b = make_env(cfg, state, hf)
+        b.single_launch = False
+        b.refresh_buffers()
+        for step in range(3):
+            a.fused_pre_reset()
+            b.fused_pre_reset()
+            ka, kb = int(a._n_reset.item()), int(b._n_reset.item())
+            assert ka == kb and ka > 0
+            assert torch.equal(a._reset_ids[:ka], b._reset_ids[:kb])
+            assert torch.equal(a._reset_ids[:ka], a.reset_buf.nonzero(as_tuple=False).flatten())
+            assert torch.equal(a._term_priv[:ka], b._term_priv[:kb])
+            assert torch.equal(a._term_amp[:ka], b._term_amp[:kb])
+            # ... and to the two stand-alone kernels (hl_select_reset_ids, hl_terminal_rows)
+            from isaacgymloco_b200 import _lib as L
+            ids2 = torch.full((n,), -1, dtype=torch.long, device="cuda")
+            cnt2 = torch.zeros(1, dtype=torch.int32, device="cuda")
+            L.check(L.lib.hl_select_reset_ids(L.ptr(b.reset_buf), n, L.ptr(ids2), L.ptr(cnt2), None, L.stream()))
+            assert int(cnt2.item()) == kb and torch.equal(ids2[:kb], b._reset_ids[:kb])
+            rows_b = b._term_priv[:kb].clone()
+            rows2 = b.compute_termination_observations(ids2[:kb])
+            assert torch.equal(rows2, rows_b)
+            a.fused_post_reset(with_reset_zero=True)
+            b.fused_post_reset(with_reset_zero=True)
+            a.common_step_counter += 1
+            b.common_step_counter += 1
+        sa, sb = a.snapshot(), b.snapshot()
+        for k in sa:
+            assert torch.equal(sa[k], sb[k]), k
