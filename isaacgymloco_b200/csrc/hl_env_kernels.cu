@@ -869,10 +869,10 @@ extern "C" int hl_select_reset_ids(const uint8_t* reset_buf, int64_t n, int64_t*
 //            privileged_obs[0:51], the last_* roll (skipped for envs that reset: the post-reset
 //            fix-up redoes it after reset_idx).
 #ifndef HL_EPB
-#define HL_EPB 32
+#define HL_EPB 64
 #endif
 #ifndef HL_SCALAR_WARPS
-#define HL_SCALAR_WARPS 1
+#define HL_SCALAR_WARPS 2
 #endif
 constexpr int EPB = HL_EPB;
 constexpr int FUSED_THREADS = 256;
@@ -1559,8 +1559,9 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
     }
   }
   int rc;
+  const bool fast = P > 160 && P <= 192 && PB <= 64 && !hclip;
 #define HL_LAUNCH(CPU, NI, NB, HC) launch_fused<CPU, NI, NB, HC>(cfg, bufs, n, fa, smem, st)
-  if (P > 160 && P <= 192 && PB <= 64 && !hclip) {
+  if (fast) {
     rc = cpu ? HL_LAUNCH(true, 6, 2, false) : HL_LAUNCH(false, 6, 2, false);
   } else {
     rc = cpu ? HL_LAUNCH(true, 8, 8, true) : HL_LAUNCH(false, 8, 8, true);
