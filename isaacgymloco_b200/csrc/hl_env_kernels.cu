@@ -958,7 +958,7 @@ struct FusedArgs {
   HlPhiloxKeys keys;      // Philox round keys of bufs.philox_seed (host-computed: constant-bank operands)
 };
 
-template <bool CPU_MATH, int NIT, int NBIT, bool HCLIP>
+template <bool CPU_MATH, int NIT, int NBIT, bool HCLIP, bool COMPACT>
 __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel(HlCfg c, HlEnvBuffers b, long long n, FusedArgs fa) {
 #ifdef HL_EXP_NO_BASE
   const int cf_stride = fa.cf_stride, need_ldp = fa.need_ldp, need_ltq = fa.need_ltq, want_base = 0;
@@ -979,7 +979,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
   unsigned* ctrl = reinterpret_cast<unsigned*>(b.fused_ws);
   volatile unsigned long long* lb_state = reinterpret_cast<volatile unsigned long long*>(b.fused_ws) + 2;
   const unsigned vb = blockIdx.x;
-  if (fa.compact && tid == 0) {
+  if (COMPACT && tid == 0) {
     sm.epoch = *reinterpret_cast<volatile unsigned*>(ctrl + 2) + 1u;   // visible after the phase-0 barrier
     sm.cnt_reset = 0;
     sm.arrive = 0;
@@ -1127,7 +1127,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
       b.reset_buf[ge] = s.reset;
       b.time_out_buf[ge] = s.time_out;
       sm.reset[e] = s.reset;
-      if (fa.compact) {
+      if (COMPACT) {
         const int wc = __popc(__ballot_sync(__activemask(), s.reset));
         if (lane == 0) {
           atomicAdd(&sm.cnt_reset, wc);
@@ -1207,7 +1207,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
     if (want_base) {
       // 63-point base scans (LR:1357-1398) of all this warp's envs, batched: every gather of a batch
       // is in flight before the first is consumed
-      constexpr int BB = ENVS_PER_SCAN_WARP < 6 ? ENVS_PER_SCAN_WARP : 6;
+#ifndef HL_BASE_BATCH
+#define HL_BASE_BATCH 1
+#endif
+      constexpr int BB = ENVS_PER_SCAN_WARP < HL_BASE_BATCH ? ENVS_PER_SCAN_WARP : HL_BASE_BATCH;
       for (int l0 = 0; sw + SCAN_WARPS * l0 < cnt; l0 += BB) {
         int hraw[BB][NBIT];
 #pragma unroll
@@ -1390,7 +1393,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
   // ---------------- phase 3 (single-launch mode): env_ids = reset_buf.nonzero() (LR:225) by a
   // decoupled look-back over the CTAs, then compute_termination_observations / terminal AMP rows
   // (LR:227-228) of this CTA's reset envs straight from shared memory.
-  if (fa.compact) {
+  if (COMPACT) {
     const unsigned nblocks = gridDim.x;
     if (wid == 0) {
       const unsigned ep = sm.epoch;
@@ -1486,10 +1489,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel
   }
 }
 
-template <bool CPU_MATH, int NIT, int NBIT, bool HCLIP>
+template <bool CPU_MATH, int NIT, int NBIT, bool HCLIP, bool COMPACT>
 static int launch_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, const FusedArgs& fa, size_t smem,
                         cudaStream_t stream) {
-  auto kern = hl_post_physics_fused_kernel<CPU_MATH, NIT, NBIT, HCLIP>;
+  auto kern = hl_post_physics_fused_kernel<CPU_MATH, NIT, NBIT, HCLIP, COMPACT>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1560,7 +1563,8 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
   }
   int rc;
   const bool fast = P > 160 && P <= 192 && PB <= 64 && !hclip;
-#define HL_LAUNCH(CPU, NI, NB, HC) launch_fused<CPU, NI, NB, HC>(cfg, bufs, n, fa, smem, st)
+#define HL_LAUNCH(CPU, NI, NB, HC) (fa.compact ? launch_fused<CPU, NI, NB, HC, true>(cfg, bufs, n, fa, smem, st) \
+                                              : launch_fused<CPU, NI, NB, HC, false>(cfg, bufs, n, fa, smem, st))
   if (fast) {
     rc = cpu ? HL_LAUNCH(true, 6, 2, false) : HL_LAUNCH(false, 6, 2, false);
   } else {
