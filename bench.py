@@ -189,11 +189,17 @@ class Workload:
         env.common_step_counter += 1
         self.launches += env.cfg_hot.decimation + (2 if env.single_launch else 3)
 
-    def rollout(self, time_fused=False):
+    def rollout(self, time_fused=False, finish=True):
         for _ in range(self.t_len):
             self.env_step(time_fused)
-        self.storage.compute_returns(self.last_values, self.cfg.gamma, self.cfg.lam)
+        # compute_returns = GAE scan, [all-reduce of the 3 moments when sharded], normalisation
+        self.storage.gae_scan(self.last_values, self.cfg.gamma, self.cfg.lam)
+        if finish:
+            self.finish()
         self.launches += 2
+
+    def finish(self):
+        self.storage.normalize_advantages()
 
 
 def timed(fn, iters, sync_dist):
@@ -258,10 +264,10 @@ def run_gpu_arm(args):
     fused = [a.elapsed_time(b) for a, b in wl.fused_ms]
     ms, mode = ms_direct, "direct_launch"
 
-    # ---- pass B (1 GPU): the same K rollouts replayed from ONE captured CUDA graph -- the form the
+    # ---- pass B: the same K rollouts replayed from ONE captured CUDA graph -- the form the
     # library is meant to be driven in (every entry point is capture-safe); launch overhead gone
     graph_info = None
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:
         try:
             g = torch.cuda.CUDAGraph()
             s = torch.cuda.Stream()
@@ -270,12 +276,24 @@ def run_gpu_arm(args):
                 wl.rollout()
                 torch.cuda.synchronize()
                 with torch.cuda.graph(g, stream=s):
-                    wl.rollout()
+                    wl.rollout(finish=(world == 1))     # the NCCL all-reduce stays outside the graph
             torch.cuda.current_stream().wait_stream(s)
-            for _ in range(3):
+
+            def graph_step():
+                if world > 1:
+                    comm_stream.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(comm_stream):
+                        for _ in range(20):
+                            dist.all_reduce(grads, op=dist.ReduceOp.AVG)
                 g.replay()
-            gms = timed(g.replay, args.steps, False)
-            graph_info = {"value": args.envs * args.rollout * args.steps / (gms * 1e-3), "unit": UNIT,
+                if world > 1:
+                    wl.finish()
+                    torch.cuda.current_stream().wait_stream(comm_stream)
+
+            for _ in range(3):
+                graph_step()
+            gms = timed(graph_step, args.steps, world > 1)
+            graph_info = {"value": world * args.envs * args.rollout * args.steps / (gms * 1e-3), "unit": UNIT,
                           "ms_per_step": gms / args.steps}
             if gms < ms_direct:
                 ms, mode = gms, "cuda_graph_replay"
@@ -284,6 +302,8 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if sampler else None
     value = world * args.envs * args.rollout * args.steps / (ms * 1e-3)
 
+    # ---- e2e runs on EVERY rank (it contains collectives: moment all-reduce, barriers)
+    e2e = None if args.no_e2e else measure_e2e(wl, args, world)
     if rank != 0:
         return
     peak, peak_src = peaks()
@@ -309,8 +329,8 @@ def run_gpu_arm(args):
 
     # ---- e2e: the public API with HOST buffers (pinned), H2D of the PhysX tensors + actions and
     # D2H of obs / privileged obs / rewards / dones every env-step, inside the timed region
-    if not args.no_e2e:
-        line["e2e"] = measure_e2e(wl, args, world)
+    if e2e is not None:
+        line["e2e"] = e2e
     # ---- 4096-env latency regime (configs[1]) and the CPU baseline: rank 0, N=1 only
     if world == 1:
         if not args.no_latency:
@@ -340,21 +360,39 @@ def measure_e2e(wl, args, world):
     h2d = sum(v.numel() * v.element_size() for v in host_in.values())
     d2h = sum(v.numel() * v.element_size() for v in host_out.values())
 
+    # Three streams: H2D of step t+1 and D2H of step t overlap (PCIe is full duplex); the step itself
+    # goes through the public API, including post_physics_step's host sync on the reset count.
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    ev = {"in": torch.cuda.Event(), "compute": torch.cuda.Event(), "out": torch.cuda.Event()}
+    ev["compute"].record(main)
+    ev["out"].record(main)
+
     def e2e_step():
-        for k in names_in:
-            dev_in[k].view(-1).copy_(host_in[k].view(-1), non_blocking=True)
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev["compute"])               # previous step has consumed the input tensors
+            for k in names_in:
+                dev_in[k].view(-1).copy_(host_in[k].view(-1), non_blocking=True)
+            ev["in"].record(s_in)
+        main.wait_event(ev["in"])
+        main.wait_event(ev["out"])                       # previous results are on the host: outputs may be overwritten
         env._delay_actions()
         for k in range(env.cfg_hot.decimation):
             env._compute_torques_into(env.delayed_actions[:, k], env.torques)
-        env.post_physics_step()                      # public API (includes the reference's host sync on the reset count)
-        for k, v in outs.items():
-            host_out[k].copy_(v, non_blocking=True)
+        env.post_physics_step()
+        ev["compute"].record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev["compute"])
+            for k, v in outs.items():
+                host_out[k].copy_(v, non_blocking=True)
+            ev["out"].record(s_out)
 
     def e2e_rollout():
         for _ in range(wl.t_len):
             e2e_step()
         wl.storage.compute_returns(wl.last_values, wl.cfg.gamma, wl.cfg.lam)
-        torch.cuda.current_stream().synchronize()
+        s_out.synchronize()
+        main.synchronize()
 
     e2e_rollout()
     iters = max(1, min(args.steps, 3))

@@ -11,6 +11,7 @@ distributed code at all; these are the only exchange steps the sharded path need
 All messages are <= 4.5 MB => latency-bound: one NCCL call per optimiser step on one flat buffer.
 Backend: NCCL over NVLink/NVSwitch on GPUs; gloo in the CPU tests.
 """
+import datetime
 import os
 from typing import Iterable, Optional
 
@@ -29,11 +30,13 @@ def init_from_env(backend: Optional[str] = None):
         os.environ.setdefault("MASTER_PORT", "29511")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
+        # short collective timeout: a rank that falls out of step must fail fast, not hold a GPU box
+        to = datetime.timedelta(seconds=int(os.environ.get("HL_DIST_TIMEOUT_S", "120")))
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+            dist.init_process_group(backend, rank=rank, world_size=world, timeout=to, device_id=torch.device("cuda", local))
         else:
-            dist.init_process_group(backend, rank=rank, world_size=world)
+            dist.init_process_group(backend, rank=rank, world_size=world, timeout=to)
     return rank, world, local
 
 
