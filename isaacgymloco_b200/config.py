@@ -280,7 +280,7 @@ class HotPathCfg:
         return names
 
     def noise_scale_vec(self) -> np.ndarray:     # legged_robot.py:883-910
-        n = 45 + (187 if self.measure_heights else 0)
+        n = 45 + (len(self.measured_points_x) * len(self.measured_points_y) if self.measure_heights else 0)
         v = np.zeros(n, dtype=np.float32)
         lvl = self.noise_level
         v[3:6] = self.noise_ang_vel * lvl * self.obs_ang_vel

@@ -852,7 +852,7 @@ extern "C" int hl_select_reset_ids(const uint8_t* reset_buf, int64_t n, int64_t*
 }
 
 // ============================================================================= the fused step
-// One CTA (8 warps) = EPB = 64 consecutive envs.
+// One CTA (8 warps) = EPB consecutive envs (tile sizes 64 / 52 / 32, see pick_tile).
 //   phase 0  128-bit coalesced slab loads of every AoS record into shared memory (odd row strides
 //            => conflict-free one-lane-per-env reads); only pos/vel of the 4 foot records are
 //            fetched from rigid_body_states.
@@ -868,54 +868,8 @@ extern "C" int hl_select_reset_ids(const uint8_t* reset_buf, int64_t n, int64_t*
 //   phase 2  coalesced stores: obs history shift (register-staged, in-place safe), slot 0,
 //            privileged_obs[0:51], the last_* roll (skipped for envs that reset: the post-reset
 //            fix-up redoes it after reset_idx).
-#ifndef HL_EPB
-#define HL_EPB 64
-#endif
-#ifndef HL_SCALAR_WARPS
-#define HL_SCALAR_WARPS 2
-#endif
-constexpr int EPB = HL_EPB;
-constexpr int FUSED_THREADS = 256;
-constexpr int SCALAR_WARPS = HL_SCALAR_WARPS;
-static_assert(SCALAR_WARPS * 32 >= EPB && EPB % 4 == 0 && EPB <= 64, "one lane per env; 16-B aligned slabs");
-constexpr int SCAN_WARPS = FUSED_THREADS / 32 - SCALAR_WARPS;
 constexpr int S13 = 13, SDOF = 25, SFOOT = 25, SCUR = 57;
-constexpr int ENVS_PER_SCAN_WARP = (EPB + SCAN_WARPS - 1) / SCAN_WARPS;
 
-struct FusedSmem {
-  float root[EPB * S13];
-  float dof[EPB * SDOF];
-  float foot[EPB * SFOOT];   // per env: foot f -> pos3 at [6f], vel3 at [6f+3]
-  float act[EPB * S13], lact[EPB * S13], llact[EPB * S13], ldv[EPB * S13], tq[EPB * S13];
-  float cur[EPB * SCUR];
-  float base_h[EPB];
-  unsigned char reset[EPB];
-  int cnt_reset, arrive, excl;  // single-launch compaction: resets in this CTA, scalar-warp arrivals, exclusive prefix
-  unsigned vb, epoch;           // virtual block id (ticket order) and look-back epoch
-  // dynamic tail: contact forces (EPB*cf_stride), then optional last_dof_pos / last_torques slabs
-};
-
-// global (count x REC contiguous floats, 16-B aligned slab) -> shared rows of STRIDE, float4 loads
-template <int REC, int STRIDE>
-__device__ __forceinline__ void stage_in4(float* dst, const float* __restrict__ src, int count, int tid) {
-  const int total = count * REC;
-  const int n4 = total >> 2;
-  const float4* src4 = reinterpret_cast<const float4*>(src);
-  for (int i = tid; i < n4; i += FUSED_THREADS) {
-    const float4 v = __ldg(src4 + i);
-    const int base = i << 2;
-    const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int idx = base + j, e = idx / REC, k = idx - e * REC;
-      dst[e * STRIDE + k] = vv[j];
-    }
-  }
-  for (int idx = (n4 << 2) + tid; idx < total; idx += FUSED_THREADS) {
-    const int e = idx / REC, k = idx - e * REC;
-    dst[e * STRIDE + k] = __ldg(src + idx);
-  }
-}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -958,556 +912,67 @@ struct FusedArgs {
   HlPhiloxKeys keys;      // Philox round keys of bufs.philox_seed (host-computed: constant-bank operands)
 };
 
-template <bool CPU_MATH, int NIT, int NBIT, bool HCLIP, bool COMPACT>
-__global__ void __launch_bounds__(FUSED_THREADS, 3) hl_post_physics_fused_kernel(HlCfg c, HlEnvBuffers b, long long n, FusedArgs fa) {
-#ifdef HL_EXP_NO_BASE
-  const int cf_stride = fa.cf_stride, need_ldp = fa.need_ldp, need_ltq = fa.need_ltq, want_base = 0;
-#else
-  const int cf_stride = fa.cf_stride, need_ldp = fa.need_ldp, need_ltq = fa.need_ltq, want_base = fa.want_base;
-#endif
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
-  float* s_cf = reinterpret_cast<float*>(smem_raw + sizeof(FusedSmem));
-  float* s_ldp = s_cf + EPB * cf_stride;
-  float* s_ltq = s_ldp + (need_ldp ? EPB * S13 : 0);
-  float* s_sums = s_ltq + (need_ltq ? EPB * S13 : 0);  // (R, EPB) episode sums of this block
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // Single-launch compaction: every CTA publishes its reset count early (right after
-  // termination); at its end it sums the counts of all lower-numbered CTAs.  A CTA only waits on
-  // CTAs with a smaller blockIdx, which the hardware dispatched before it, so they are running
-  // or done: no deadlock.  ws = {unused, done, epoch, pad, state[nblocks]}, state = epoch<<32 | count.
-  unsigned* ctrl = reinterpret_cast<unsigned*>(b.fused_ws);
-  volatile unsigned long long* lb_state = reinterpret_cast<volatile unsigned long long*>(b.fused_ws) + 2;
-  const unsigned vb = blockIdx.x;
-  if (COMPACT && tid == 0) {
-    sm.epoch = *reinterpret_cast<volatile unsigned*>(ctrl + 2) + 1u;   // visible after the phase-0 barrier
-    sm.cnt_reset = 0;
-    sm.arrive = 0;
-  }
-  const long long e0 = (long long)vb * EPB;
-  const int cnt = (int)((n - e0) < EPB ? (n - e0) : EPB);
-  const int B = c.num_bodies, P = c.n_px * c.n_py, PD = 51 + P;
+// tile sizes: 64 (default), 52 (65,536 envs = 1261 CTAs = 2.84 waves of 444 instead of 2.31 -> 3
+// waves of 52 instead of 64 envs), 32 (small shards: more CTAs than SMs sooner)
+#define FK_NS fk64
+#define FK_EPB 64
+#define FK_SCALAR_WARPS 2
+#define FK_GENERIC 1   // also the any-grid / clipped-heights fallback
+#define FK_COMPACT 1
+#include "hl_fused_kernel.inc"
+#undef FK_NS
+#undef FK_EPB
+#undef FK_SCALAR_WARPS
+#undef FK_GENERIC
+#undef FK_COMPACT
+#define FK_NS fk52
+#define FK_EPB 52
+#define FK_SCALAR_WARPS 2
+#define FK_GENERIC 0
+#define FK_COMPACT 0
+#include "hl_fused_kernel.inc"
+#undef FK_NS
+#undef FK_EPB
+#undef FK_SCALAR_WARPS
+#undef FK_GENERIC
+#undef FK_COMPACT
+#define FK_NS fk32
+#define FK_EPB 32
+#define FK_SCALAR_WARPS 1
+#define FK_GENERIC 0
+#define FK_COMPACT 1
+#include "hl_fused_kernel.inc"
+#undef FK_NS
+#undef FK_EPB
+#undef FK_SCALAR_WARPS
+#undef FK_GENERIC
+#undef FK_COMPACT
 
-  // ---------------- phase 0: stage inputs.  Every load of the block is issued before the first
-  // shared-memory store (all requests in flight at once: ~40 KB per CTA), 128-bit where the slab
-  // is 16-B aligned.
-  const int R = c.n_terms + c.has_termination_term;
-  {
-    const float4* root4 = reinterpret_cast<const float4*>(b.root_states + e0 * 13);
-    const float4* dof4 = reinterpret_cast<const float4*>(b.dof_state + e0 * 24);
-    const float4* cf4p = reinterpret_cast<const float4*>(b.contact_forces + e0 * B * 3);
-    const float4* a4[5] = {reinterpret_cast<const float4*>(b.actions + e0 * 12), reinterpret_cast<const float4*>(b.last_actions + e0 * 12),
-                           reinterpret_cast<const float4*>(b.last_last_actions + e0 * 12),
-                           reinterpret_cast<const float4*>(b.last_dof_vel + e0 * 12), reinterpret_cast<const float4*>(b.torques + e0 * 12)};
-    float* a_dst[5] = {sm.act, sm.lact, sm.llact, sm.ldv, sm.tq};
-    const int n_root = (cnt * 13) >> 2, n_dof = (cnt * 24) >> 2, n_cf = (cnt * B * 3) >> 2, n_a = (cnt * 12) >> 2;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 r_root = tid < n_root ? __ldg(root4 + tid) : z4;
-    constexpr int NJ_DOF = (EPB * 6 + FUSED_THREADS - 1) / FUSED_THREADS;        // float4s per thread
-    constexpr int NJ_CF = (EPB * 51 / 4 + FUSED_THREADS - 1) / FUSED_THREADS;    // sized for 17 bodies; more -> leftover loop
-    constexpr int NJ_FOOT = (EPB * 24 + FUSED_THREADS - 1) / FUSED_THREADS;
-    static_assert(EPB * 3 <= FUSED_THREADS && EPB * 13 / 4 < FUSED_THREADS, "one float4 per thread for the 12/13-wide slabs");
-    float4 r_dof[NJ_DOF], r_cf[NJ_CF], r_a[5];
-#pragma unroll
-    for (int j = 0; j < NJ_DOF; ++j) r_dof[j] = tid + j * FUSED_THREADS < n_dof ? __ldg(dof4 + tid + j * FUSED_THREADS) : z4;
-#pragma unroll
-    for (int j = 0; j < NJ_CF; ++j) r_cf[j] = tid + j * FUSED_THREADS < n_cf ? __ldg(cf4p + tid + j * FUSED_THREADS) : z4;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) r_a[j] = tid < n_a ? __ldg(a4[j] + tid) : z4;
-    float r_foot[NJ_FOOT];
-#pragma unroll
-    for (int j = 0; j < NJ_FOOT; ++j) {  // pos/vel of the 4 foot records only
-      const int i = tid + j * FUSED_THREADS;
-      const int e = i / 24, r = i - e * 24, f = r / 6, k = r - f * 6;
-      r_foot[j] = i < cnt * 24 ? __ldg(b.rigid_body_states + ((e0 + e) * B + c.feet_idx[f]) * 13 + (k < 3 ? k : k + 4)) : 0.f;
-    }
-    // episode sums rows (R x cnt), coalesced per row
-    for (int i = tid; i < R * EPB; i += FUSED_THREADS) {
-      const int k = i / EPB, e = i - k * EPB;
-      if (e < cnt && b.episode_sums) s_sums[i] = __ldg(b.episode_sums + (long long)k * n + e0 + e);
-    }
-    // commit to shared memory (odd row strides)
-    auto put4 = [](float* dst, int stride, int rec, int i4, const float4& v) {
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-      int e = (i4 << 2) / rec, k = (i4 << 2) - e * rec;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        dst[e * stride + k] = vv[j];
-        if (++k == rec) { k = 0; ++e; }
-      }
-    };
-    if (tid < n_root) put4(sm.root, S13, 13, tid, r_root);
-#pragma unroll
-    for (int j = 0; j < NJ_DOF; ++j) if (tid + j * FUSED_THREADS < n_dof) put4(sm.dof, SDOF, 24, tid + j * FUSED_THREADS, r_dof[j]);
-#pragma unroll
-    for (int j = 0; j < NJ_CF; ++j)
-      if (tid + j * FUSED_THREADS < n_cf) {
-        if (B == 17) put4(s_cf, 51, 51, tid + j * FUSED_THREADS, r_cf[j]);  // aliengo: constant divisor
-        else put4(s_cf, cf_stride, B * 3, tid + j * FUSED_THREADS, r_cf[j]);
-      }
-#pragma unroll
-    for (int j = 0; j < 5; ++j) if (tid < n_a) put4(a_dst[j], S13, 12, tid, r_a[j]);
-#pragma unroll
-    for (int j = 0; j < NJ_FOOT; ++j) {
-      const int i = tid + j * FUSED_THREADS;
-      if (i < cnt * 24) sm.foot[(i / 24) * SFOOT + (i % 24)] = r_foot[j];
-    }
-    // leftovers: contact slabs beyond NJ_CF float4 per thread (more bodies) and ragged tails
-    for (int i4 = tid + NJ_CF * FUSED_THREADS; i4 < n_cf; i4 += FUSED_THREADS) put4(s_cf, cf_stride, B * 3, i4, __ldg(cf4p + i4));
-    for (int idx = (n_root << 2) + tid; idx < cnt * 13; idx += FUSED_THREADS) sm.root[(idx / 13) * S13 + idx % 13] = __ldg(b.root_states + e0 * 13 + idx);
-    for (int idx = (n_cf << 2) + tid; idx < cnt * B * 3; idx += FUSED_THREADS)
-      s_cf[(idx / (B * 3)) * cf_stride + idx % (B * 3)] = __ldg(b.contact_forces + e0 * B * 3 + idx);
-    if (need_ldp) stage_in4<12, S13>(s_ldp, b.last_dof_pos + e0 * 12, cnt, tid);
-    if (need_ltq) stage_in4<12, S13>(s_ltq, b.last_torques + e0 * 12, cnt, tid);
+// Envs per CTA that minimises (waves x tile cost) for this shard on this device: a wave is
+// SMs x 3 resident CTAs; the cost of a tile is ~ a fixed part (loads, barriers) + its envs.
+static int pick_tile(int64_t n) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
-  __syncthreads();
-
-  if (wid < SCALAR_WARPS) {
-    // ---------------- phase 1a: one lane per env
-    const int e = tid;
-    const bool act_lane = e < cnt;
-    const long long ge = e0 + (act_lane ? e : 0);
-    EnvView v;
-    EnvScalars s;
-    if (act_lane) {
-      v.root = sm.root + e * S13;
-      v.dof = sm.dof + e * SDOF;
-      v.cf = s_cf + e * cf_stride;
-      for (int f = 0; f < 4; ++f) {
-        v.fpos[f] = sm.foot + e * SFOOT + f * 6;
-        v.fvel[f] = v.fpos[f] + 3;
-      }
-      v.act = sm.act + e * S13;
-      v.lact = sm.lact + e * S13;
-      v.llact = sm.llact + e * S13;
-      v.ldp = s_ldp + e * S13;
-      v.ldv = sm.ldv + e * S13;
-      v.tq = sm.tq + e * S13;
-      v.ltq = s_ltq + e * S13;
-      s.gid = ge + c.env_id_offset;
-      s.feet_shift = 0;
-      s.base_h = 0.0f;
-      // independent global loads first (all in flight together)
-      const long long tl = b.terrain_levels ? __ldg(b.terrain_levels + ge) : 0;
-      const long long epl = b.episode_length_buf[ge];
-      const float4 cm = reinterpret_cast<const float4*>(b.commands)[ge];
-      const float4 ar = reinterpret_cast<const float4*>(b.feet_air_time)[ge];
-      const unsigned lc4 = reinterpret_cast<const unsigned*>(b.last_contacts)[ge];
-      float* dptr = b.disturbance + ge * B * 3;
-      const float d0 = dptr[0], d1 = dptr[1], d2 = dptr[2];
-      s.terrain_level = tl;
-      s.ep_len = epl + 1;  // LR:193
-      s.cmd[0] = cm.x; s.cmd[1] = cm.y; s.cmd[2] = cm.z; s.cmd[3] = cm.w;
-      s.air[0] = ar.x; s.air[1] = ar.y; s.air[2] = ar.z; s.air[3] = ar.w;
-      unsigned last = 0;
-#pragma unroll
-      for (int f = 0; f < 4; ++f) last |= (((lc4 >> (8 * f)) & 0xffu) ? 1u : 0u) << f;
-      hl_frame(v, s);
-      hl_contacts(c, v, last, s);
-      if (c.heading_command) s.cmd[2] = hl_heading_command(v.root + 3, s.cmd[3]);
-      // one-step observation without noise (the scan warps add noise, clip and store it)
-      float* cur = sm.cur + e * SCUR;
-#pragma unroll
-      for (int k = 0; k < 45; ++k) cur[k] = hl_obs45(c, v, s, k);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) cur[45 + k] = s.blv[k] * c.obs_lin_vel;
-      cur[48] = d0; cur[49] = d1; cur[50] = d2;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {  // raw velocities for the terminal AMP rows
-        cur[51 + k] = s.blv[k];
-        cur[54 + k] = s.bav[k];
-      }
-    }
-    __threadfence_block();
-    named_bar_arrive(2, FUSED_THREADS);  // sm.cur is ready for the scan warps
-    if (act_lane) {
-      hl_check_termination(c, v, s);
-      b.episode_length_buf[ge] = s.ep_len;
-      b.commands[ge * 4 + 2] = s.cmd[2];
-      b.reset_buf[ge] = s.reset;
-      b.time_out_buf[ge] = s.time_out;
-      sm.reset[e] = s.reset;
-      if (COMPACT) {
-        const int wc = __popc(__ballot_sync(__activemask(), s.reset));
-        if (lane == 0) {
-          atomicAdd(&sm.cnt_reset, wc);
-          __threadfence_block();
-          const int live_warps = (cnt + 31) >> 5;
-          if (atomicAdd(&sm.arrive, 1) == live_warps - 1) {  // last scalar warp: publish this CTA's aggregate
-            const int tot = atomicAdd(&sm.cnt_reset, 0);
-            lb_state[vb] = ((unsigned long long)sm.epoch << 32) | (unsigned)tot;
-            __threadfence();
-          }
-        }
-      }
-      if (!s.reset) {  // LR:235; reset envs: the fix-up still reads the disturbance, then zeroes it
-        float* dptr = b.disturbance + ge * B * 3;
-        dptr[0] = 0.0f; dptr[1] = 0.0f; dptr[2] = 0.0f;
-      }
-      unsigned cf4 = 0;
-#pragma unroll
-      for (int f = 0; f < 4; ++f) cf4 |= ((s.cfilt >> f) & 1u) << (8 * f);
-      reinterpret_cast<unsigned*>(b.contact_filt)[ge] = cf4;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        b.base_lin_vel[ge * 3 + k] = s.blv[k];
-        b.base_ang_vel[ge * 3 + k] = s.bav[k];
-        b.projected_gravity[ge * 3 + k] = s.pg[k];
-      }
-    }
-    if (want_base) named_bar_sync(1, FUSED_THREADS);  // base heights are in shared memory
-    if (act_lane) {
-      s.base_h = sm.base_h[e];
-#ifdef HL_EXP_NO_REWARD
-      const float rew = 0.0f;
-#else
-      const float rew = hl_compute_reward(c, b, v, s, b.episode_sums ? s_sums + e : nullptr, EPB, true);
-#endif
-      b.rew_buf[ge] = rew;
-      unsigned lc = 0;
-#pragma unroll
-      for (int f = 0; f < 4; ++f) lc |= ((s.last_contact >> f) & 1u) << (8 * f);
-      reinterpret_cast<unsigned*>(b.last_contacts)[ge] = lc;
-      reinterpret_cast<float4*>(b.feet_air_time)[ge] = make_float4(s.air[0], s.air[1], s.air[2], s.air[3]);
-    }
-  } else {
-    // ---------------- phase 1b: one warp per env: scans + every row-shaped output of the env
-    const int sw = wid - SCALAR_WARPS;
-    const int16_t* __restrict__ min3 = b.height_min3;
-    const int pitch = c.terrain_cols - 1;
-    const bool plane = c.mesh_type == 0;
-    // this lane's grid points (body frame) and noise scales, fixed for the whole kernel
-    float gx[NIT], gy[NIT], hx[NBIT], hy[NBIT];
-    // p / n via float reciprocal: exact for p < 256 (checked on the host: P, PB <= 256)
-    const float inv_npy = 1.0f / (float)c.n_py, inv_nby = 1.0f / (float)c.n_by;
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int p = min(it * 32 + lane, P - 1), i = (int)(((float)p + 0.5f) * inv_npy), j = p - i * c.n_py;
-      gx[it] = c.px[i];
-      gy[it] = c.py[j];
-    }
-    const int PB = c.n_bx * c.n_by;
-#pragma unroll
-    for (int it = 0; it < NBIT; ++it) {
-      const int p = min(it * 32 + lane, PB - 1), i = (int)(((float)p + 0.5f) * inv_nby), j = p - i * c.n_by;
-      hx[it] = c.bx[i];
-      hy[it] = c.by[j];
-    }
-    const HlPhiloxKeys& keys = fa.keys;
-    const float nv0 = c.add_noise ? c.noise45[lane] : 0.0f;
-    const float nv1 = (c.add_noise && lane < 13) ? c.noise45[32 + lane] : 0.0f;
-    int cb, c0;
-    hl_cur_noise_slot(P, cb, c0);
-    // yaw quaternions of this warp's envs: lane l normalises env sw + SCAN_WARPS*l, broadcast later
-    float qz_l = 0.0f, qw_l = 1.0f;
-    {
-      const int e = sw + SCAN_WARPS * lane;
-      if (lane < ENVS_PER_SCAN_WARP && e < cnt) hl_yaw_quat(sm.root + e * S13 + 3, qz_l, qw_l);
-    }
-    if (want_base) {
-      // 63-point base scans (LR:1357-1398) of all this warp's envs, batched: every gather of a batch
-      // is in flight before the first is consumed
-#ifndef HL_BASE_BATCH
-#define HL_BASE_BATCH 1
-#endif
-      constexpr int BB = ENVS_PER_SCAN_WARP < HL_BASE_BATCH ? ENVS_PER_SCAN_WARP : HL_BASE_BATCH;
-      for (int l0 = 0; sw + SCAN_WARPS * l0 < cnt; l0 += BB) {
-        int hraw[BB][NBIT];
-#pragma unroll
-        for (int q = 0; q < BB; ++q) {
-          const int e = sw + SCAN_WARPS * (l0 + q);
-          const float qz = __shfl_sync(0xffffffffu, qz_l, l0 + q), qw = __shfl_sync(0xffffffffu, qw_l, l0 + q);
-          const float* root = sm.root + (e < cnt ? e : sw) * S13;
-          const float posx = root[0], posy = root[1];
-#pragma unroll
-          for (int it = 0; it < NBIT; ++it)
-            hraw[q][it] = (plane || e >= cnt) ? 0 : scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, posx, posy, hx[it], hy[it]);
-        }
-#pragma unroll
-        for (int q = 0; q < BB; ++q) {
-          const int e = sw + SCAN_WARPS * (l0 + q);
-          if (e < cnt) {   // warp-uniform
-            const float posz = sm.root[e * S13 + 2];
-            float acc = 0.0f;
-#pragma unroll
-            for (int it = 0; it < NBIT; ++it)
-              if (it * 32 + lane < PB) acc += posz - (float)hraw[q][it] * c.vertical_scale;
-            acc = warp_sum(acc);
-            if (lane == 0) sm.base_h[e] = plane ? posz : acc / (float)PB;
-          }
-        }
-      }
-      __threadfence_block();
-      named_bar_arrive(1, FUSED_THREADS);
-    }
-#ifdef HL_EXP_NO_PHILOX
-    const bool philox = false, philox45 = false;
-#else
-    const bool philox = c.add_noise && !b.noise_u187;
-    const bool philox45 = c.add_noise && !b.noise_u45;
-#endif
-    const float cl = c.clip_obs;
-    constexpr int NPASS = (NIT + 3) / 4;
-    // height obs = clamp(z - 0.5 - h, +-1) * s + (2u - 1) * nh  (LR:399-400); with u = k * 2^-24 the
-    // noise is one FFMA: k * (nh * 2^-23) - nh.  |value| <= s + nh, so the +-clip_obs clip of step()
-    // is dropped when it cannot bind.
-    const float nh = c.add_noise ? c.noise_height : 0.0f;
-    const float nh_scale = nh * (1.0f / 8388608.0f);
-    // software pipeline: the gathers of the next env are in flight while this one is written out
-    int hnext[NIT];
-    {
-      const float* root = sm.root + sw * S13;
-      const float qz = __shfl_sync(0xffffffffu, qz_l, 0), qw = __shfl_sync(0xffffffffu, qw_l, 0);
-      const float px0 = root[0], py0 = root[1];
-#pragma unroll
-      for (int it = 0; it < NIT; ++it)
-        hnext[it] = (plane || sw >= cnt) ? 0 : scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, px0, py0, gx[it], gy[it]);
-    }
-    named_bar_sync(2, FUSED_THREADS);  // one-step observations are in shared memory
-    for (int li = 0, e = sw; e < cnt; e += SCAN_WARPS, ++li) {
-      const long long ge = e0 + e;
-      // row pointers of this env, lane offset folded in (64-bit math once per env)
-      const float* hsrc = b.obs_buf_in + ge * 270 + lane;
-      float* hdst = b.obs_buf_out + ge * 270 + lane;
-      float* mptr = b.measured_heights + ge * P + lane;
-      float* pptr = b.privileged_obs_buf + ge * PD + lane;
-      // obs history (independent of everything else): loads first
-      float old[8];
-#pragma unroll
-      for (int i = 0; i < 7; ++i) old[i] = hsrc[i * 32];
-      old[7] = lane < 1 ? hsrc[224] : 0.0f;
-      int hraw[NIT];
-#pragma unroll
-      for (int it = 0; it < NIT; ++it) hraw[it] = hnext[it];
-      const int en = e + SCAN_WARPS;
-      if (en < cnt && !plane) {
-        const float* rootn = sm.root + en * S13;
-        const float qz = __shfl_sync(0xffffffffu, qz_l, li + 1), qw = __shfl_sync(0xffffffffu, qw_l, li + 1);
-        const float pxn = rootn[0], pyn = rootn[1];
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) hnext[it] = scan_gather<CPU_MATH>(c, min3, pitch, qz, qw, pxn, pyn, gx[it], gy[it]);
-      }
-      const float rz05 = sm.root[e * S13 + 2] - 0.5f;
-      uint4 nz[NPASS];
-      uint4 nzx = make_uint4(0u, 0u, 0u, 0u);
-      if (philox || philox45) {
-        const unsigned long long genv = (unsigned long long)(ge + c.env_id_offset);
-#pragma unroll
-        for (int a = 0; a < NPASS; ++a) nz[a] = hl_noise_block(keys, b.philox_offset, genv, (unsigned)(a * 32 + lane), 0u);
-        if (cb >= NPASS) nzx = hl_noise_block(keys, b.philox_offset, genv, (unsigned)(cb * 32 + lane), 0u);
-      }
-      const float* urow = b.noise_u187 ? b.noise_u187 + ge * P + lane : nullptr;
-#pragma unroll
-      for (int it = 0; it < NIT; ++it) {
-        // only the last iteration can run past P on the fast path (host guarantees P > 32*(NIT-1) there)
-        if (it < NIT - 1 && NIT == 6 ? true : (it * 32 + lane < P)) {
-          const float mh = (float)hraw[it] * c.vertical_scale;
-          float nzv;
-          if (philox) nzv = fmaf((float)(hl_pick(nz[it >> 2], it & 3) >> 8), nh_scale, -nh);
-          else nzv = urow ? (2.0f * urow[it * 32] - 1.0f) * nh : 0.0f;
-          float hv = fmaf(hl_clampf(rz05 - mh, -1.0f, 1.0f), c.obs_height, nzv);
-          if (HCLIP) hv = hl_clampf(hv, -cl, cl);
-#ifndef HL_EXP_NO_HOUT
-          mptr[it * 32] = mh;
-          pptr[51 + it * 32] = hv;
-#else
-          if (hv == 123.456f) mptr[it * 32] = mh;
-#endif
-        }
-      }
-      // slot 0 of obs_buf and privileged_obs[0:51]: noise, clip (LR:394,167-171)
-      {
-        const float* cur = sm.cur + e * SCUR;
-        float x0 = cur[lane], x1 = lane < 19 ? cur[32 + lane] : 0.0f;
-        float u0 = 0.5f, u1 = 0.5f;
-        if (philox45) {
-          uint4 q = nzx;
-#pragma unroll
-          for (int a = 0; a < NPASS; ++a)
-            if (cb == a) q = nz[a];
-          u0 = hl_u01(hl_pick(q, c0));
-          u1 = hl_u01(hl_pick(q, c0 + 1));
-        } else if (b.noise_u45) {
-          u0 = b.noise_u45[ge * 45 + lane];
-          if (lane < 13) u1 = b.noise_u45[ge * 45 + 32 + lane];
-        }
-        x0 = hl_clampf(x0 + (2.0f * u0 - 1.0f) * nv0, -cl, cl);
-        x1 = hl_clampf(x1 + (2.0f * u1 - 1.0f) * nv1, -cl, cl);
-        hdst[0] = x0;
-        pptr[0] = x0;
-        if (lane < 13) hdst[32] = x1;
-        if (lane < 19) pptr[32] = x1;
-      }
-      // history shift (register-staged: in-place safe); LR:168 clips the whole buffer
-      if (!fa.hist_clipped) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) old[i] = hl_clampf(old[i], -cl, cl);
-      }
-#ifndef HL_EXP_NO_HIST
-#pragma unroll
-      for (int i = 0; i < 7; ++i) hdst[45 + i * 32] = old[i];
-      if (lane < 1) hdst[45 + 224] = old[7];
-#endif
-    }
+  const char* fe = getenv("HL_FUSED_EPB");  // dev/test knob, read per call
+  const int forced = fe ? atoi(fe) : 0;
+  if (forced == 64 || forced == 52 || forced == 32) return forced;
+  const int cand[3] = {64, 52, 32};
+  int best = 64;
+  double best_cost = 1e30;
+  for (int k = 0; k < 3; ++k) {
+    const int64_t ctas = (n + cand[k] - 1) / cand[k];
+    const int64_t waves = (ctas + (int64_t)sms * 3 - 1) / ((int64_t)sms * 3);
+    const double cost = (double)waves * (10.0 + cand[k]);
+    if (cost < best_cost) { best_cost = cost; best = cand[k]; }
   }
-  __syncthreads();
-
-  // ---------------- phase 2: episode sums write-back and the end-of-step roll
-  if (b.episode_sums)
-    for (int i = tid; i < R * EPB; i += FUSED_THREADS) {
-      const int k = i / EPB, e = i - k * EPB;
-      if (e < cnt) b.episode_sums[(long long)k * n + e0 + e] = s_sums[i];
-    }
-  // LR:235-241 for the envs that do not reset: one 128-bit store per (env, third of a row)
-#ifdef HL_EXP_NO_ROLL
-  if (tid < 0) {
-#else
-  if (tid < cnt * 3) {
-#endif
-    const int e = tid / 3, q = tid - e * 3;
-    if (!sm.reset[e]) {
-      const int so = e * S13 + q * 4;
-      const long long go = (e0 + e) * 3 + q;
-      reinterpret_cast<float4*>(b.last_last_actions)[go] = make_float4(sm.lact[so], sm.lact[so + 1], sm.lact[so + 2], sm.lact[so + 3]);
-      reinterpret_cast<float4*>(b.last_actions)[go] = make_float4(sm.act[so], sm.act[so + 1], sm.act[so + 2], sm.act[so + 3]);
-      reinterpret_cast<float4*>(b.last_torques)[go] = make_float4(sm.tq[so], sm.tq[so + 1], sm.tq[so + 2], sm.tq[so + 3]);
-      const float* d = sm.dof + e * SDOF + q * 8;
-      reinterpret_cast<float4*>(b.last_dof_pos)[go] = make_float4(d[0], d[2], d[4], d[6]);
-      reinterpret_cast<float4*>(b.last_dof_vel)[go] = make_float4(d[1], d[3], d[5], d[7]);
-      if (q < 2) {  // last_root_vel: 6 floats per env = 3 float2
-        const float* rv = sm.root + e * S13 + 7;
-        float2* dst2 = reinterpret_cast<float2*>(b.last_root_vel) + (e0 + e) * 3;
-        dst2[q] = make_float2(rv[2 * q], rv[2 * q + 1]);
-        if (q == 0) dst2[2] = make_float2(rv[4], rv[5]);
-      }
-    }
-  }
-  if (b.feet_pos || b.feet_vel) {
-    for (int i = tid; i < cnt * 12; i += FUSED_THREADS) {
-      const int e = i / 12, r = i - e * 12, f = r / 3, k = r - f * 3;
-      if (b.feet_pos) b.feet_pos[e0 * 12 + i] = sm.foot[e * SFOOT + f * 6 + k];
-      if (b.feet_vel) b.feet_vel[e0 * 12 + i] = sm.foot[e * SFOOT + f * 6 + 3 + k];
-    }
-  }
-
-  // ---------------- phase 3 (single-launch mode): env_ids = reset_buf.nonzero() (LR:225) by a
-  // decoupled look-back over the CTAs, then compute_termination_observations / terminal AMP rows
-  // (LR:227-228) of this CTA's reset envs straight from shared memory.
-  if (COMPACT) {
-    const unsigned nblocks = gridDim.x;
-    if (wid == 0) {
-      const unsigned ep = sm.epoch;
-      int acc = 0;
-      for (unsigned base = 0; base < vb; base += 32 * 8) {  // 8 independent loads per lane in flight
-        unsigned long long w[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const unsigned j = base + u * 32 + lane;
-          w[u] = j < vb ? lb_state[j] : ((unsigned long long)ep << 32);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const unsigned j = base + u * 32 + lane;
-          while ((unsigned)(w[u] >> 32) != ep) w[u] = lb_state[j];   // predecessor has not published yet
-          acc += (int)(unsigned)w[u];
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) {
-        sm.excl = acc;
-        if (vb == nblocks - 1) *b.n_reset_out = acc + sm.cnt_reset;
-      }
-    }
-    __syncthreads();
-    if (sm.cnt_reset > 0) {
-      const int excl = sm.excl;
-      int cbn, c0n;
-      hl_cur_noise_slot(P, cbn, c0n);
-      const float nh = c.add_noise ? c.noise_height : 0.0f;
-      // the reset envs of this CTA as two ballot masks; warp w takes the w-th, (w+8)-th, ... of them
-      const unsigned m0 = __ballot_sync(0xffffffffu, lane < cnt && sm.reset[lane]);
-      const unsigned m1 = __ballot_sync(0xffffffffu, lane + 32 < cnt && sm.reset[lane + 32]);
-      const int n0 = __popc(m0), ntot = n0 + __popc(m1);
-      for (int r = wid; r < ntot; r += FUSED_THREADS / 32) {
-        // env index of the r-th set bit
-        unsigned m = r < n0 ? m0 : m1;
-        int skip = r < n0 ? r : r - n0;
-        while (skip--) m &= m - 1;
-        const int e = (__ffs(m) - 1) + (r < n0 ? 0 : 32);
-        const long long ge = e0 + e, row = excl + r;
-        const unsigned long long genv = (unsigned long long)(ge + c.env_id_offset);
-        if (lane == 0) b.reset_ids_out[row] = ge;
-        const float* cur = sm.cur + e * SCUR;
-        float* out = b.term_priv_out + row * PD;
-        uint4 nb = make_uint4(0u, 0u, 0u, 0u);
-        if (c.add_noise && !b.term_noise_u45) nb = hl_noise_block(fa.keys, b.philox_offset, genv, (unsigned)(cbn * 32 + lane), 1u);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int k = lane + 32 * h;
-          if (k < 51) {
-            float x = cur[k];
-            if (k < 45 && c.add_noise) {
-              const float u = b.term_noise_u45 ? b.term_noise_u45[ge * 45 + k] : hl_u01(hl_pick(nb, c0n + h));
-              x += (2.0f * u - 1.0f) * c.noise45[k];
-            }
-            out[k] = x;
-          }
-        }
-        const float rz = sm.root[e * S13 + 2];
-        uint4 hb = make_uint4(0u, 0u, 0u, 0u);
-        for (int it = 0; it * 32 < P; ++it) {
-          const int p = it * 32 + lane;
-          if (c.add_noise && !b.term_noise_u187 && (it & 3) == 0)
-            hb = hl_noise_block(fa.keys, b.philox_offset, genv, (unsigned)((it >> 2) * 32 + lane), 1u);
-          if (p < P) {
-            float u = 0.5f;
-            if (c.add_noise) u = b.term_noise_u187 ? b.term_noise_u187[ge * P + p] : hl_u01(hl_pick(hb, it & 3));
-            const float mh = b.measured_heights[ge * P + p];  // written by this CTA's scan warps
-            out[51 + p] = hl_clampf(rz - 0.5f - mh, -1.0f, 1.0f) * c.obs_height + (2.0f * u - 1.0f) * nh;
-          }
-        }
-        if (b.term_amp_out && lane < 30) {  // LR:416: dof_pos 12, base_lin_vel 3, base_ang_vel 3, dof_vel 12
-          float x;
-          if (lane < 12) x = sm.dof[e * SDOF + 2 * lane];
-          else if (lane < 18) x = cur[51 + (lane - 12)];
-          else x = sm.dof[e * SDOF + 2 * (lane - 18) + 1];
-          b.term_amp_out[row * 30 + lane] = x;
-        }
-      }
-    }
-    // the last CTA to finish re-arms the workspace for the next launch (CUDA-graph safe: no memset)
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      if (atomicAdd(ctrl + 1, 1u) == nblocks - 1) {
-        ctrl[1] = 0u;
-        ctrl[2] = sm.epoch;
-        __threadfence();
-      }
-    }
-  }
+  return best;
 }
 
-template <bool CPU_MATH, int NIT, int NBIT, bool HCLIP, bool COMPACT>
-static int launch_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, const FusedArgs& fa, size_t smem,
-                        cudaStream_t stream) {
-  auto kern = hl_post_physics_fused_kernel<CPU_MATH, NIT, NBIT, HCLIP, COMPACT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) {
-      hl_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return HL_E_CUDA;
-    }
-    attr_set = true;
-  }
-  const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
-  kern<<<blocks, FUSED_THREADS, smem, stream>>>(*cfg, *bufs, n, fa);
-  return HL_OK;
-}
-
-extern "C" int64_t hl_fused_workspace_bytes(int64_t n) { return (int64_t)(((n + EPB - 1) / EPB) + 2) * 8; }
+extern "C" int64_t hl_fused_workspace_bytes(int64_t n) { return (int64_t)(((n + 32 - 1) / 32) + 2) * 8; }  // sized for the smallest tile
 
 extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, void* stream) {
   if (int r = check_cfg(cfg, bufs)) return r;
@@ -1536,9 +1001,6 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
     need_ltq |= cfg->term_id[k] == T_torques_dif;
     want_base |= cfg->term_id[k] == T_base_height || cfg->term_id[k] == T_base_height_up;
   }
-  const size_t smem = sizeof(FusedSmem) + (size_t)EPB * (cf_stride + (need_ldp ? S13 : 0) + (need_ltq ? S13 : 0) +
-                                                          cfg->n_terms + cfg->has_termination_term) * sizeof(float);
-  HL_CHECK_ARG(smem <= 200 * 1024, "num_bodies too large for the shared-memory slab");
   const int P = cfg->n_px * cfg->n_py, PB = cfg->n_bx * cfg->n_by;
   const bool cpu = cfg->index_math == HL_INDEX_MATH_TORCH_CPU;
   const cudaStream_t st = (cudaStream_t)stream;
@@ -1561,16 +1023,12 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
       y += 0xBB67AE85u;
     }
   }
-  int rc;
   const bool fast = P > 160 && P <= 192 && PB <= 64 && !hclip;
-#define HL_LAUNCH(CPU, NI, NB, HC) (fa.compact ? launch_fused<CPU, NI, NB, HC, true>(cfg, bufs, n, fa, smem, st) \
-                                              : launch_fused<CPU, NI, NB, HC, false>(cfg, bufs, n, fa, smem, st))
-  if (fast) {
-    rc = cpu ? HL_LAUNCH(true, 6, 2, false) : HL_LAUNCH(false, 6, 2, false);
-  } else {
-    rc = cpu ? HL_LAUNCH(true, 8, 8, true) : HL_LAUNCH(false, 8, 8, true);
-  }
-#undef HL_LAUNCH
+  const int tile = pick_tile(n);
+  int rc = HL_E_UNSUPPORTED;
+  if (tile == 52) rc = fk52::run(cfg, bufs, n, fa, fast, cpu, st);
+  else if (tile == 32) rc = fk32::run(cfg, bufs, n, fa, fast, cpu, st);
+  if (rc == HL_E_UNSUPPORTED) rc = fk64::run(cfg, bufs, n, fa, fast, cpu, st);
   if (rc) return rc;
   HL_CHECK_LAUNCH();
   return HL_OK;

@@ -180,7 +180,7 @@ def make_state(cfg: HotPathCfg, n: int, hf: torch.Tensor, seed: int = 1234, step
         dist[:, 0, :] = (rand(n, 3) * 2 - 1) * 30.0
     s["disturbance"] = dist
     s["obs_buf"] = randn(n, 270).clamp(-cfg.clip_observations, cfg.clip_observations)
-    s["privileged_obs_buf"] = randn(n, 238)
+    s["privileged_obs_buf"] = randn(n, 51 + len(cfg.measured_points_x) * len(cfg.measured_points_y))
     s["base_lin_vel"] = torch.zeros(n, 3)
     s["base_ang_vel"] = torch.zeros(n, 3)
     s["projected_gravity"] = torch.zeros(n, 3)
@@ -195,12 +195,12 @@ def make_state(cfg: HotPathCfg, n: int, hf: torch.Tensor, seed: int = 1234, step
     return s
 
 
-def make_noise(n: int, seed: int = 99) -> Dict[str, torch.Tensor]:
+def make_noise(n: int, seed: int = 99, n_points: int = 187) -> Dict[str, torch.Tensor]:
     """Pre-drawn U[0,1) tensors standing in for the four `torch.rand_like` draws of one
     post_physics_step (legged_robot.py:451,457 terminal obs; :394,400 obs), in call order."""
     g = torch.Generator().manual_seed(seed)
-    return dict(term45=torch.rand(n, 45, generator=g), term187=torch.rand(n, 187, generator=g),
-                obs45=torch.rand(n, 45, generator=g), obs187=torch.rand(n, 187, generator=g))
+    return dict(term45=torch.rand(n, 45, generator=g), term187=torch.rand(n, n_points, generator=g),
+                obs45=torch.rand(n, 45, generator=g), obs187=torch.rand(n, n_points, generator=g))
 
 
 def make_reset_targets(cfg: HotPathCfg, state: Dict[str, torch.Tensor], hf: torch.Tensor,

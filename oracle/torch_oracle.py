@@ -458,7 +458,7 @@ class OracleEnv:
         if c.measure_heights:
             h = torch.clip(self.root_states[:, 2].unsqueeze(1) - 0.5 - self.measured_heights, -1, 1.0) \
                 * c.obs_height
-            h += (2 * u187 - 1) * self.noise_scale_vec[45:45 + 187]
+            h += (2 * u187 - 1) * self.noise_scale_vec[45:45 + h.shape[1]]
             cur = torch.cat((cur, h), dim=-1)
         return cur
 
@@ -466,11 +466,11 @@ class OracleEnv:
         """LR:382-404."""
         cur = self._current_obs(u45, u187)
         self.obs_buf = torch.cat((cur[:, :45], self.obs_buf[:, :-45]), dim=-1)
-        self.privileged_obs_buf = cur[:, :238].clone()
+        self.privileged_obs_buf = cur.clone()
 
     def compute_termination_observations(self, env_ids, u45, u187):
         """LR:439-460."""
-        return self._current_obs(u45, u187)[:, :238][env_ids]
+        return self._current_obs(u45, u187)[env_ids]
 
     def get_amp_observations(self):
         """LR:406-416."""

@@ -280,3 +280,51 @@ def test_single_launch_equals_separate_kernels():
         sa, sb = a.snapshot(), b.snapshot()
         for k in sa:
             assert torch.equal(sa[k], sb[k]), k
+
+
+@pytest.mark.parametrize("tile", ["64", "52", "32"])
+def test_every_tile_size_vs_oracle(tile, monkeypatch):
+    """The fused kernel is instantiated for 64/52/32 envs per CTA (wave quantisation); force each
+    and compare with the oracle, ragged env count (tail CTA) included."""
+    from gpu_helpers import assert_close, assert_equal, compare_snapshots, make_env
+    from isaacgymloco_b200 import config as C, synthetic as S
+    monkeypatch.setenv("HL_FUSED_EPB", tile)
+    n = 3000 + 7
+    cfg = C.aliengo("stairs", num_envs=n)
+    hf = S.make_terrain(cfg, seed=3)
+    state = S.make_state(cfg, n, hf, seed=41)
+    noise = S.make_noise(n, seed=42)
+    targets = S.make_reset_targets(cfg, state, hf, seed=43)
+    oenv, oids, oterm, oamp = _oracle_step(cfg, state, hf, noise, targets, "cuda")
+    for single in (True, False):
+        env = make_env(cfg, state, hf, targets, noise)
+        env.single_launch = single
+        env.refresh_buffers()
+        ids, term_obs, term_amp = env.post_physics_step()
+        assert_equal(ids, oids, "env_ids")
+        assert_close(term_obs, oterm, "termination_privileged_obs")
+        assert_close(term_amp, oamp, "terminal_amp_states")
+        compare_snapshots(env.snapshot(), oenv.snapshot())
+
+
+def test_generic_grid_and_clipped_heights_path():
+    """A non-reference scan grid (9 x 7 = 63 points) and a clip that binds on the height
+    observations take the generic (any grid, clip compiled in) instantiation."""
+    from gpu_helpers import assert_close, assert_equal, compare_snapshots, make_env
+    from isaacgymloco_b200 import config as C, synthetic as S
+    n = 2048
+    for kw in (dict(measured_points_x=[-0.6, -0.45, -0.3, -0.15, 0., 0.15, 0.3, 0.45, 0.6],
+                    measured_points_y=[-0.3, -0.2, -0.1, 0., 0.1, 0.2, 0.3]),
+               dict(clip_observations=3.0)):
+        cfg = C.aliengo("flat", num_envs=n, **kw)
+        p = len(cfg.measured_points_x) * len(cfg.measured_points_y)
+        hf = S.make_terrain(cfg, seed=4)
+        state = S.make_state(cfg, n, hf, seed=51)
+        noise = S.make_noise(n, seed=52, n_points=p)
+        oenv, oids, oterm, oamp = _oracle_step(cfg, state, hf, noise, None, "cuda")
+        env = make_env(cfg, state, hf, None, noise)
+        ids, term_obs, term_amp = env.post_physics_step()
+        assert env.privileged_obs_buf.shape[1] == 51 + p
+        assert_equal(ids, oids, "env_ids")
+        assert_close(term_obs, oterm, "termination_privileged_obs")
+        compare_snapshots(env.snapshot(), oenv.snapshot())
