@@ -25,6 +25,35 @@ void hl_set_error(const char* fmt, ...);
     }                                                                            \
   } while (0)
 
+// ----------------------------------------------------------------------------- launches
+// Programmatic dependent launch (griddepcontrol, sm_90+): the kernels of one env step form a chain
+// of short dependent launches (4 x torque, fused, select/terminal, fix-up), so each kernel lets
+// its successor be scheduled right away and then waits for its predecessor's memory: launch
+// latency and the first wave's ramp-up overlap the predecessor's tail.  Every kernel launched
+// through hl_launch() calls hl_pdl_enter() before its first global access and before any return.
+__device__ __forceinline__ void hl_pdl_enter() {
+#ifdef HL_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool hl_pdl_enabled();  // HL_PDL=0 turns the launch attribute off (A/B runs)
+
+template <typename... KArgs, typename... Args>
+static inline void hl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = grid;
+  lc.blockDim = block;
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = hl_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&lc, kern, static_cast<KArgs>(args)...);   // errors surface in HL_CHECK_LAUNCH
+}
+
 // ----------------------------------------------------------------------------- reward term ids
 // sorted() order of the 51 unique `_reward_*` names (legged_robot.py:1444-1770); mirrored by
 // isaacgymloco_b200/config.py::REWARD_TERMS.

@@ -15,6 +15,13 @@ void hl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* hl_last_error(void) { return g_err; }
+bool hl_pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("HL_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 extern "C" int hl_version(void) { return HL_VERSION; }
 extern "C" int hl_sizeof_cfg(void) { return (int)sizeof(HlCfg); }
 extern "C" int hl_sizeof_env_buffers(void) { return (int)sizeof(HlEnvBuffers); }
@@ -61,6 +68,7 @@ __global__ void __launch_bounds__(128) hl_pd_torque_vec_kernel(PdCfg c, const fl
                                                                const float* __restrict__ kp, const float* __restrict__ kd,
                                                                const float4* __restrict__ last_dof_vel, float4* __restrict__ out,
                                                                float4* __restrict__ target_out, long long n) {
+  hl_pdl_enter();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   const float4* a4 = reinterpret_cast<const float4*>(actions + e * a_stride);
@@ -95,6 +103,7 @@ __global__ void __launch_bounds__(256) hl_pd_torque_kernel(PdCfg c, const float*
                                                            const float* __restrict__ last_dof_vel,
                                                            float* __restrict__ out, float* __restrict__ target_out,
                                                            long long total) {
+  hl_pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long e = i / 12;
@@ -128,12 +137,12 @@ extern "C" int hl_pd_torque(const HlCfg* cfg, const float* actions, int64_t a_st
   const bool vec = al16(actions) && (a_stride % 4 == 0) && al16(dof_state) && al16(motor_strength) && al16(torques_out) &&
                    (!target_out || al16(target_out)) && (!last_dof_vel || al16(last_dof_vel));
   if (vec) {
-    hl_pd_torque_vec_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+    hl_launch(hl_pd_torque_vec_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, (cudaStream_t)stream,
         pc, actions, a_stride, (const float4*)dof_state, (const float4*)motor_strength, kp, kd, (const float4*)last_dof_vel,
         (float4*)torques_out, (float4*)target_out, n);
   } else {
     const long long total = n * 12;
-    hl_pd_torque_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    hl_launch(hl_pd_torque_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
         pc, actions, a_stride, (const float2*)dof_state, motor_strength, kp, kd, last_dof_vel, torques_out, target_out, total);
   }
   HL_CHECK_LAUNCH();
@@ -281,6 +290,7 @@ template <unsigned STAGES>  // 0 = take the mask at run time; otherwise everythi
 __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, unsigned stages_rt,
                                                        const long long* __restrict__ ids,
                                                        const int* __restrict__ n_ids, long long n) {
+  hl_pdl_enter();
   const unsigned stages = STAGES ? STAGES : stages_rt;
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -503,11 +513,11 @@ static int launch_stage(const HlCfg* cfg, const HlEnvBuffers* bufs, unsigned sta
   constexpr unsigned FIX = HL_ST_HEIGHTS | HL_ST_OBS | HL_ST_OBS_NOSHIFT | HL_ST_OBS_CLIP | HL_ST_ROLL;
   const cudaStream_t st = (cudaStream_t)stream;
   if (stages == FIX)
-    hl_stage_kernel<FIX><<<(unsigned)blocks, 256, 0, st>>>(*cfg, *bufs, stages, (const long long*)ids, n_ids, n);
+    hl_launch(hl_stage_kernel<FIX>, dim3((unsigned)blocks), dim3(256), 0, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n);
   else if (stages == (FIX | HL_ST_RESET_ZERO))
-    hl_stage_kernel<FIX | HL_ST_RESET_ZERO><<<(unsigned)blocks, 256, 0, st>>>(*cfg, *bufs, stages, (const long long*)ids, n_ids, n);
+    hl_launch(hl_stage_kernel<FIX | HL_ST_RESET_ZERO>, dim3((unsigned)blocks), dim3(256), 0, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n);
   else
-    hl_stage_kernel<0u><<<(unsigned)blocks, 256, 0, st>>>(*cfg, *bufs, stages, (const long long*)ids, n_ids, n);
+    hl_launch(hl_stage_kernel<0u>, dim3((unsigned)blocks), dim3(256), 0, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n);
   HL_CHECK_LAUNCH();
   return HL_OK;
 }
@@ -535,6 +545,7 @@ __global__ void __launch_bounds__(256) hl_terminal_rows_kernel(HlCfg c, HlEnvBuf
                                                                const float* __restrict__ u187,
                                                                float* __restrict__ out_priv, float* __restrict__ out_amp,
                                                                long long n) {
+  hl_pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -600,8 +611,8 @@ extern "C" int hl_terminal_rows(const HlCfg* cfg, const HlEnvBuffers* bufs, cons
   if (int r = check_cfg(cfg, bufs)) return r;
   HL_CHECK_ARG(env_ids && n_ids_dev && out_priv, "null pointer");
   if (n <= 0) return HL_OK;
-  hl_terminal_rows_kernel<<<(unsigned)((n * 32 + 255) / 256 < 148 * 8 ? (n * 32 + 255) / 256 : 148 * 8), 256, 0, (cudaStream_t)stream>>>(*cfg, *bufs, (const long long*)env_ids, n_ids_dev, u45,
-                                                                 u187, out_priv, out_amp, n);
+  hl_launch(hl_terminal_rows_kernel, dim3((unsigned)((n * 32 + 255) / 256 < 148 * 8 ? (n * 32 + 255) / 256 : 148 * 8)), dim3(256), 0,
+            (cudaStream_t)stream, *cfg, *bufs, (const long long*)env_ids, n_ids_dev, u45, u187, out_priv, out_amp, n);
   HL_CHECK_LAUNCH();
   return HL_OK;
 }
@@ -622,6 +633,7 @@ __global__ void __launch_bounds__(256) hl_select_terminal_kernel(HlCfg c, HlEnvB
   __shared__ int s_excl, s_total;
   __shared__ unsigned s_epoch;
   __shared__ int s_local[SEL_ENVS];  // local env offsets of this CTA's reset envs, ascending
+  hl_pdl_enter();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned vb = blockIdx.x, nblocks = gridDim.x;
   unsigned* ctrl = reinterpret_cast<unsigned*>(ws);
@@ -754,8 +766,8 @@ extern "C" int hl_select_and_terminal(const HlCfg* cfg, const HlEnvBuffers* bufs
   if (int r = check_cfg(cfg, bufs)) return r;
   HL_CHECK_ARG(ids_out && count_out && workspace && bufs->reset_buf, "null pointer");
   if (n <= 0) return HL_OK;
-  hl_select_terminal_kernel<<<(unsigned)((n + SEL_ENVS - 1) / SEL_ENVS), 256, 0, (cudaStream_t)stream>>>(
-      *cfg, *bufs, u45, u187, (long long*)ids_out, count_out, out_priv, out_amp, (unsigned long long*)workspace, n);
+  hl_launch(hl_select_terminal_kernel, dim3((unsigned)((n + SEL_ENVS - 1) / SEL_ENVS)), dim3(256), 0, (cudaStream_t)stream,
+            *cfg, *bufs, u45, u187, (long long*)ids_out, count_out, out_priv, out_amp, (unsigned long long*)workspace, n);
   HL_CHECK_LAUNCH();
   return HL_OK;
 }
