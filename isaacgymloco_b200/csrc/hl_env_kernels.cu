@@ -880,7 +880,7 @@ extern "C" int hl_select_reset_ids(const uint8_t* reset_buf, int64_t n, int64_t*
 //   phase 2  coalesced stores: obs history shift (register-staged, in-place safe), slot 0,
 //            privileged_obs[0:51], the last_* roll (skipped for envs that reset: the post-reset
 //            fix-up redoes it after reset_idx).
-constexpr int S13 = 13, SDOF = 25, SFOOT = 25, SCUR = 57;
+constexpr int S13 = 13, SA = 12, SDOF = 24, SFOOT = 25, SCUR = 57;   // shared-memory row strides (floats)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -891,7 +891,7 @@ template <bool CPU_MATH>
 __device__ __forceinline__ int cell32(float world, float border, float hs, float inv_hs, int hi) {
   const float p = __fadd_rn(world, border);
   const float g = CPU_MATH ? __fdiv_rn(p, hs) : __fmul_rn(p, inv_hs);
-  return min(max(__float2int_rz(g), 0), hi);
+  return (int)min(__float2uint_rz(g), (unsigned)hi);   // cvt.rzi.u32 saturates: negatives and NaN -> 0
 }
 
 // raw min-of-3 height (int16 units) under body-frame point (bx,by): quat_apply_yaw + translate +
@@ -919,6 +919,7 @@ __device__ __forceinline__ int scan_gather(const HlCfg& c, const int16_t* __rest
 
 struct FusedArgs {
   int cf_stride, need_ldp, need_ltq, want_base;
+  int sums_aligned;       // episode_sums rows are 16-B aligned per block (n % 4 == 0, base aligned)
   int compact;            // emit reset ids / count / terminal rows from this launch (decoupled look-back)
   int hist_clipped;       // obs history is known to be within +-clip_obs already (every step after the first)
   HlPhiloxKeys keys;      // Philox round keys of bufs.philox_seed (host-computed: constant-bank operands)
@@ -1005,8 +1006,7 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
     for (const void* q : al) HL_CHECK_ARG(((uintptr_t)q & 15) == 0, "state tensors must be 16-byte aligned");
   }
   if (n <= 0) return HL_OK;
-  int cf_stride = cfg->num_bodies * 3;
-  if ((cf_stride & 1) == 0) cf_stride += 1;
+  const int cf_stride = cfg->num_bodies * 3;   // dense slab
   int need_ldp = 0, need_ltq = 0, want_base = 0;
   for (int k = 0; k < cfg->n_terms; ++k) {
     need_ldp |= cfg->term_id[k] == T_dof_pos_dif;
@@ -1023,6 +1023,7 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
   fa.need_ldp = need_ldp;
   fa.need_ltq = need_ltq;
   fa.want_base = want_base;
+  fa.sums_aligned = (n % 4 == 0) && (((uintptr_t)b.episode_sums & 15) == 0);
   fa.hist_clipped = (int)(b.flags & HL_BUF_HISTORY_CLIPPED);
   fa.compact = b.reset_ids_out != nullptr;
   HL_CHECK_ARG(!fa.compact || (b.n_reset_out && b.term_priv_out && b.fused_ws), "single-launch mode needs n_reset_out, term_priv_out, fused_ws");

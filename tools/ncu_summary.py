@@ -105,11 +105,24 @@ def sass_join(rep, so, kernel_re, n_envs):
            "stall reasons: " + ", ".join(f"{s[6:]} {100*v/tst:.1f}%" for s, v in sorted(agg.items(), key=lambda x: -x[1])[:8]),
            "opcodes/env: " + ", ".join(f"{k} {v/n_envs:.0f}" for k, v in op.most_common(16)), "hot source lines (warp-inst/env, stall-sample share):"]
     src = {}
-    for f in ("hl_env_kernels.cu", "hl_math.cuh", "hl_common.cuh"):
+    for f in ("hl_env_kernels.cu", "hl_math.cuh", "hl_common.cuh", "hl_fused_kernel.inc"):
         src[f] = open(os.path.join(os.path.dirname(so), "csrc", f)).read().split("\n")
-    for fl, nn in byline.most_common(40):
+    for fl, nn in byline.most_common(int(os.environ.get("TOPN", 40))):
         s = src.get(fl[0], [""] * 10000)[fl[1] - 1].strip()[:80] if fl and fl[0] in src else ""
         out.append(f"  {nn/n_envs:7.1f} {100*samp[fl]/ts:5.1f}%  {fl[0] if fl else '?'}:{fl[1] if fl else 0:4d}  {s}")
+    # per-file totals and, for the fused kernel body, per-phase totals (markers in the source)
+    perfile = collections.Counter()
+    for fl, nn in byline.items():
+        perfile[fl[0] if fl else "?"] += nn
+    out.append("per file (warp-inst/env): " + ", ".join(f"{k} {v/n_envs:.0f}" for k, v in perfile.most_common()))
+    inc = src.get("hl_fused_kernel.inc")
+    if inc:
+        marks = [(i + 1, l.strip()[:60]) for i, l in enumerate(inc) if "// ----------------" in l]
+        marks = [(0, "prologue")] + marks + [(10 ** 9, "")]
+        for (a, name), (b_, _) in zip(marks[:-1], marks[1:]):
+            tot_r = sum(nn for fl, nn in byline.items() if fl and fl[0] == "hl_fused_kernel.inc" and a <= fl[1] < b_)
+            sm_r = sum(nn for fl, nn in samp.items() if fl and fl[0] == "hl_fused_kernel.inc" and a <= fl[1] < b_)
+            out.append(f"  .inc lines {a:4d}-: {tot_r/n_envs:7.1f} inst/env, {100*sm_r/ts:5.1f}% samples  {name}")
     return "\n".join(out)
 
 
