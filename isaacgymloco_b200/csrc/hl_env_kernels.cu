@@ -286,6 +286,59 @@ __device__ __forceinline__ int hl_priv_dim(const HlCfg& c) { return 51 + (c.meas
 // One warp per env (optionally per listed env id); scalars are computed redundantly by all lanes,
 // vector work (scan, obs rows) is lane-parallel.  Serves the individual drop-in methods and the
 // post-reset fix-up; the hot path is hl_post_physics_fused_kernel below.
+// Per-warp staging of one env's records: lane-parallel, coalesced loads that are all in flight
+// together (one DRAM round trip), then the per-env math reads shared memory.  Layout (floats):
+// root 13 | dof 24 | feet 4 x (pos3, vel3) | act, lact, llact, ldp, ldv, tq, ltq 7 x 12 | cf B*3
+constexpr int WS_ROOT = 0, WS_DOF = 13, WS_FEET = 37, WS_A = 61, WS_CF = 145;
+__host__ __device__ inline int hl_warp_stage_floats(int num_bodies) { return (WS_CF + num_bodies * 3 + 3) & ~3; }
+
+__device__ __forceinline__ void hl_stage_env(float* st, const HlCfg& c, const HlEnvBuffers& b, long long e, int lane,
+                                             bool zero_last, EnvView& v) {
+  const int B = c.num_bodies;
+  const float r_root = (lane < 13 && b.root_states) ? b.root_states[e * 13 + lane] : 0.0f;
+  const float r_dof = (lane < 24 && b.dof_state) ? b.dof_state[e * 24 + lane] : 0.0f;
+  float r_feet = 0.0f;
+  if (lane < 24 && b.rigid_body_states) {
+    const int f = lane / 6, k = lane - f * 6;
+    r_feet = b.rigid_body_states[(e * B + c.feet_idx[f]) * 13 + (k < 3 ? k : k + 4)];
+  }
+  const float* a_src[7] = {b.actions, b.last_actions, b.last_last_actions, b.last_dof_pos, b.last_dof_vel, b.torques, b.last_torques};
+  float r_a[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const bool last = j == 1 || j == 2 || j == 3 || j == 4 || j == 6;   // zeroed by reset_idx (LR:323-329)
+    r_a[j] = (lane < 12 && a_src[j] && !(zero_last && last)) ? a_src[j][e * 12 + lane] : 0.0f;
+  }
+  float r_cf[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r_cf[j] = (lane + 32 * j < B * 3 && b.contact_forces) ? b.contact_forces[e * B * 3 + lane + 32 * j] : 0.0f;
+  if (lane < 13) st[WS_ROOT + lane] = r_root;
+  if (lane < 24) st[WS_DOF + lane] = r_dof;
+  if (lane < 24) st[WS_FEET + lane] = r_feet;
+#pragma unroll
+  for (int j = 0; j < 7; ++j)
+    if (lane < 12) st[WS_A + 12 * j + lane] = r_a[j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (lane + 32 * j < B * 3) st[WS_CF + lane + 32 * j] = r_cf[j];
+  for (int i = lane + 128; i < B * 3; i += 32) st[WS_CF + i] = b.contact_forces ? b.contact_forces[e * B * 3 + i] : 0.0f;
+  __syncwarp();
+  v.root = st + WS_ROOT;
+  v.dof = st + WS_DOF;
+  v.cf = st + WS_CF;
+  for (int f = 0; f < 4; ++f) {
+    v.fpos[f] = st + WS_FEET + 6 * f;
+    v.fvel[f] = v.fpos[f] + 3;
+  }
+  v.act = st + WS_A;
+  v.lact = st + WS_A + 12;
+  v.llact = st + WS_A + 24;
+  v.ldp = st + WS_A + 36;
+  v.ldv = st + WS_A + 48;
+  v.tq = st + WS_A + 60;
+  v.ltq = st + WS_A + 72;
+}
+
 template <unsigned STAGES>  // 0 = take the mask at run time; otherwise everything else is compiled out
 __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, unsigned stages_rt,
                                                        const long long* __restrict__ ids,
@@ -299,24 +352,14 @@ __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, 
   const int B = c.num_bodies;
   const int P = c.n_px * c.n_py;
   const int PD = hl_priv_dim(c);
+  extern __shared__ __align__(16) float stage_smem[];
+  float* st = stage_smem + (threadIdx.x >> 5) * hl_warp_stage_floats(B);
   for (long long it0 = warp0; it0 < items; it0 += nwarps) {
     const long long e = ids ? ids[it0] : it0;
     if (e < 0 || e >= n) continue;
+    __syncwarp();   // the previous env's staged records are no longer read
     EnvView v;
-    v.root = b.root_states + e * 13;
-    v.dof = b.dof_state + e * 24;
-    v.cf = b.contact_forces + e * B * 3;
-    for (int f = 0; f < 4; ++f) {
-      v.fpos[f] = b.rigid_body_states + (e * B + c.feet_idx[f]) * 13;
-      v.fvel[f] = v.fpos[f] + 7;
-    }
-    v.act = b.actions + e * 12;
-    v.lact = b.last_actions + e * 12;
-    v.llact = b.last_last_actions + e * 12;
-    v.ldp = b.last_dof_pos + e * 12;
-    v.ldv = b.last_dof_vel + e * 12;
-    v.tq = b.torques + e * 12;
-    v.ltq = b.last_torques + e * 12;
+    hl_stage_env(st, c, b, e, lane, (stages & HL_ST_RESET_ZERO) != 0, v);
     if (stages & HL_ST_RESET_ZERO) {  // LR:323-329,350,361
       if (lane < 12) {
         b.last_actions[e * 12 + lane] = 0.0f;
@@ -510,14 +553,16 @@ static int launch_stage(const HlCfg* cfg, const HlEnvBuffers* bufs, unsigned sta
   if (n <= 0) return HL_OK;
   long long blocks = (n * 32 + 255) / 256;
   if (ids) blocks = blocks < 148 * 8 ? blocks : 148 * 8;  // id lists are short; grid-stride covers the rest
+  const size_t stage_smem = (size_t)8 * hl_warp_stage_floats(cfg->num_bodies) * sizeof(float);
+  HL_CHECK_ARG(stage_smem <= 48 * 1024, "num_bodies too large for the per-warp staging area");
   constexpr unsigned FIX = HL_ST_HEIGHTS | HL_ST_OBS | HL_ST_OBS_NOSHIFT | HL_ST_OBS_CLIP | HL_ST_ROLL;
   const cudaStream_t st = (cudaStream_t)stream;
   if (stages == FIX)
-    hl_launch(hl_stage_kernel<FIX>, dim3((unsigned)blocks), dim3(256), 0, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n);
+    hl_launch(hl_stage_kernel<FIX>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n);
   else if (stages == (FIX | HL_ST_RESET_ZERO))
-    hl_launch(hl_stage_kernel<FIX | HL_ST_RESET_ZERO>, dim3((unsigned)blocks), dim3(256), 0, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n);
+    hl_launch(hl_stage_kernel<FIX | HL_ST_RESET_ZERO>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n);
   else
-    hl_launch(hl_stage_kernel<0u>, dim3((unsigned)blocks), dim3(256), 0, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n);
+    hl_launch(hl_stage_kernel<0u>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n);
   HL_CHECK_LAUNCH();
   return HL_OK;
 }
@@ -536,6 +581,21 @@ extern "C" int hl_post_reset_fixup(const HlCfg* cfg, const HlEnvBuffers* bufs, c
                       env_ids, n_ids_dev, n, stream);
 }
 
+// one env's records for the terminal rows (root 13 | dof 24 | act 12), staged per warp
+constexpr int TR_FLOATS = 52;
+__device__ __forceinline__ void hl_stage_rows_env(float* st, const HlEnvBuffers& b, long long e, int lane, EnvView& v) {
+  const float r_root = lane < 13 ? b.root_states[e * 13 + lane] : 0.0f;
+  const float r_dof = lane < 24 ? b.dof_state[e * 24 + lane] : 0.0f;
+  const float r_act = lane < 12 ? b.actions[e * 12 + lane] : 0.0f;
+  if (lane < 13) st[lane] = r_root;
+  if (lane < 24) st[13 + lane] = r_dof;
+  if (lane < 12) st[37 + lane] = r_act;
+  __syncwarp();
+  v.root = st;
+  v.dof = st + 13;
+  v.act = st + 37;
+}
+
 // ============================================================================= terminal rows
 // compute_termination_observations(env_ids) + get_amp_observations()[env_ids] (LR:227-228):
 // one warp per reset env, from the persisted pre-reset derived state.
@@ -551,13 +611,14 @@ __global__ void __launch_bounds__(256) hl_terminal_rows_kernel(HlCfg c, HlEnvBuf
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long items = *n_ids;
   const int B = c.num_bodies, P = c.n_px * c.n_py, PD = hl_priv_dim(c);
+  __shared__ float tr_stage[8 * TR_FLOATS];
+  float* st = tr_stage + (threadIdx.x >> 5) * TR_FLOATS;
   for (long long r = warp0; r < items; r += nwarps) {
     const long long e = ids[r];
     if (e < 0 || e >= n) continue;
+    __syncwarp();
     EnvView v;
-    v.root = b.root_states + e * 13;
-    v.dof = b.dof_state + e * 24;
-    v.act = b.actions + e * 12;
+    hl_stage_rows_env(st, b, e, lane, v);
     EnvScalars s;
     s.gid = e + c.env_id_offset;
     for (int k = 0; k < 4; ++k) s.cmd[k] = b.commands[e * 4 + k];
@@ -664,6 +725,15 @@ __global__ void __launch_bounds__(256) hl_select_terminal_kernel(HlCfg c, HlEnvB
   int pos = wbase + incl - cnt;
   if (mask) s_local[pos] = tid;
   __syncthreads();
+  // warps 1..7 stage the records of their first reset env while warp 0 does the look-back
+  __shared__ float tr_stage[8 * TR_FLOATS];
+  float* st = tr_stage + wid * TR_FLOATS;
+  EnvView v;
+  bool staged = false;
+  if (out_priv && wid != 0 && wid < s_total) {
+    hl_stage_rows_env(st, b, e0 + s_local[wid], lane, v);
+    staged = true;
+  }
   if (wid == 0) {  // exclusive prefix = sum of the counts of all lower CTAs
     const unsigned ep = s_epoch;
     int acc = 0;
@@ -698,10 +768,10 @@ __global__ void __launch_bounds__(256) hl_select_terminal_kernel(HlCfg c, HlEnvB
     hl_cur_noise_slot(P, cb, c0);
     for (int i = wid; i < total; i += 8) {
       const long long e = e0 + s_local[i], r = excl + i;
-      EnvView v;
-      v.root = b.root_states + e * 13;
-      v.dof = b.dof_state + e * 24;
-      v.act = b.actions + e * 12;
+      if (!(staged && i == wid)) {
+        __syncwarp();
+        hl_stage_rows_env(st, b, e, lane, v);
+      }
       EnvScalars s;
       s.gid = e + c.env_id_offset;
       for (int k = 0; k < 4; ++k) s.cmd[k] = b.commands[e * 4 + k];
