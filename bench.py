@@ -335,6 +335,7 @@ def run_gpu_arm(args):
     if world == 1:
         if not args.no_latency:
             line["latency_4096"] = measure_latency_4096(args)
+            line["next_rows"] = {"record_transition": measure_record_transition(args, peak)}
         if not args.no_cpu:
             fn, cores = cpu_rollout_runner(4096, args.rollout)
             fn()
@@ -400,6 +401,33 @@ def measure_e2e(wl, args, world):
     return {"value": world * args.envs * wl.t_len * iters / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * wl.t_len,
             "d2h_bytes_per_step": d2h * wl.t_len, "rollouts": iters, "ms_per_step": ms / iters,
             "api": "FusedLeggedRobot._compute_torques x4 + post_physics_step per env-step, HIMRolloutStorage.compute_returns per rollout"}
+
+
+def measure_record_transition(args, peak_gbs):
+    """SURVEY.md §8f rank 1 (runner patch + process_env_step + add_transitions as one launch): a pure
+    HBM copy, reported beside the headline as its own roofline line (not part of `value`)."""
+    from isaacgymloco_b200 import roofline as R, synthetic as S
+    from isaacgymloco_b200.rollout_storage import HIMRolloutStorage
+    n, t_len, dev = args.envs, 4, torch.device("cuda", torch.cuda.current_device())
+    st = HIMRolloutStorage(n, t_len, [270], [238], [12], device=dev)
+    tr = {k: v.to(dev) for k, v in S.make_transition(n, 3).items()}
+    tt = HIMRolloutStorage.Transition()
+    tt.observations, tt.critic_observations, tt.actions, tt.values = tr["obs"], tr["critic_obs"], tr["actions"], tr["values"]
+    tt.actions_log_prob, tt.action_mean, tt.action_sigma = tr["log_prob"], tr["mu"], tr["sigma"]
+    cnt = torch.tensor([tr["termination_ids"].numel()], dtype=torch.int32, device=dev)
+
+    def one():
+        st.step = st.step % t_len
+        st.record_env_step(tt, tr["rewards"], tr["dones"], {"time_outs": tr["time_outs"]}, tr["privileged_obs"],
+                           tr["termination_ids"], tr["termination_privileged_obs"], 0.99, termination_count=cnt)
+    for _ in range(3):
+        one()
+    iters = 20
+    ms = timed(one, iters, False) / iters
+    bytes_env = R.record_transition_bytes()["total"]
+    gbs = bytes_env * n / (ms * 1e-3) / 1e9
+    return {"envs": n, "us_per_step": 1e3 * ms, "bytes_per_env": bytes_env, "achieved_GBps": gbs, "peak_GBps": peak_gbs,
+            "frac": gbs / peak_gbs, "note": "slots rotate over 4 steps: 1.65 GB working set per pass, larger than L2"}
 
 
 def measure_latency_4096(args):

@@ -247,6 +247,50 @@ int hl_gae_scan(const float* rewards, const float* values, const uint8_t* dones,
                 int32_t t_len, int64_t n_envs, float gamma, float lam, void* stream);
 int hl_adv_normalize(float* advantages, const double* moments, int64_t n_elems, void* stream);
 
+/* One rollout step recorded into the time-major storage slots, fused:
+ *   runner terminal-observation patch   rsl_rl/rsl_rl/runners/him_on_policy_runner.py:122-123
+ *       next_critic_obs = critic_obs.clone(); next_critic_obs[termination_ids] = termination_privileged_obs
+ *   HIMPPO.process_env_step             rsl_rl/rsl_rl/algorithms/him_ppo.py:104-115
+ *       rewards += gamma * squeeze(values * time_outs.unsqueeze(1), 1)      (each op rounded on its own)
+ *   HIMRolloutStorage.add_transitions   rsl_rl/rsl_rl/storage/him_rollout_storage.py:92-108
+ *       the ten slot copies at `step` (dones stored as uint8)
+ * Sources are env-major device rows; `*_out` point at slot `step` of the (T,N,.) tensors.  A
+ * source/destination pair with either pointer NULL is skipped (e.g. the env already wrote that
+ * slot in place).  term_ids: ascending unique env ids (reset_buf.nonzero()), count on the device;
+ * NULL = no patch.  time_outs NULL = no bootstrap. */
+typedef struct HlTransition {
+  int32_t struct_bytes;            /* sizeof(HlTransition): ABI guard */
+  int32_t obs_dim, priv_dim, act_dim;
+  float gamma;
+  int32_t pad_;
+  const float* obs;                /* (N, obs_dim)  transition.observations            */
+  const float* critic_obs;         /* (N, priv_dim) transition.critic_observations     */
+  const float* next_critic_obs;    /* (N, priv_dim) privileged obs after the env step  */
+  const int64_t* term_ids;         /* (n_term,) or NULL                                */
+  const int32_t* n_term_dev;       /* device scalar                                    */
+  const float* term_rows;          /* (n_term, priv_dim) termination_privileged_obs    */
+  const float* actions;            /* (N, act_dim) */
+  const float* rewards;            /* (N,)         */
+  const uint8_t* dones;            /* (N,) bool/uint8 */
+  const float* values;             /* (N,1)        */
+  const uint8_t* time_outs;        /* (N,) bool/uint8 or NULL */
+  const float* log_prob;           /* (N,)         */
+  const float* mu;                 /* (N, act_dim) */
+  const float* sigma;              /* (N, act_dim) */
+  float* obs_out;
+  float* critic_out;
+  float* next_critic_out;
+  float* actions_out;
+  float* rewards_out;
+  uint8_t* dones_out;
+  float* values_out;
+  float* log_prob_out;
+  float* mu_out;
+  float* sigma_out;
+} HlTransition;
+int hl_sizeof_transition(void);
+int hl_record_transition(const HlTransition* t, int64_t n_envs, void* stream);
+
 /* AMPLoader.get_full_frame_at_time_batch(traj_idxs, times) --
  * rsl_rl/rsl_rl/datasets/motion_loader.py:231-255 with quaternion_slerp
  * rsl_rl/rsl_rl/utils/utils.py:153-186.  `frames` = all clips stacked (sum n_i, 49);

@@ -31,6 +31,15 @@ class HlEnvBuffers(ctypes.Structure):
         ("term_amp_out", _vp), ("term_noise_u45", _vp), ("term_noise_u187", _vp), ("fused_ws", _vp)]
 
 
+class HlTransition(ctypes.Structure):
+    """Mirror of `struct HlTransition` (keep field order identical to the header)."""
+    _fields_ = [("struct_bytes", c_int32), ("obs_dim", c_int32), ("priv_dim", c_int32), ("act_dim", c_int32),
+                ("gamma", c_float), ("pad_", c_int32)] + [(n, _vp) for n in (
+        "obs", "critic_obs", "next_critic_obs", "term_ids", "n_term_dev", "term_rows", "actions", "rewards", "dones",
+        "values", "time_outs", "log_prob", "mu", "sigma", "obs_out", "critic_out", "next_critic_out", "actions_out",
+        "rewards_out", "dones_out", "values_out", "log_prob_out", "mu_out", "sigma_out")]
+
+
 # stage bits (include/himloco_b200.h)
 ST_COUNTERS, ST_FRAME, ST_CONTACTS, ST_HEADING, ST_HEIGHTS = 0x001, 0x002, 0x004, 0x008, 0x010
 ST_TERMINATION, ST_REWARD, ST_OBS, ST_OBS_NOSHIFT, ST_OBS_CLIP = 0x020, 0x040, 0x080, 0x100, 0x200
@@ -55,6 +64,8 @@ EXPORTS = {
     "hl_amp_observations": (c_int32, [_vp, _vp, _vp, _vp, c_int64, _vp]),
     "hl_gae_scan": (c_int32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, c_int32, c_int64, c_float, c_float, _vp]),
     "hl_adv_normalize": (c_int32, [_vp, _vp, c_int64, _vp]),
+    "hl_sizeof_transition": (c_int32, []),
+    "hl_record_transition": (c_int32, [POINTER(HlTransition), c_int64, _vp]),
     "hl_amp_frame_blend": (c_int32, [_vp, _vp, _vp, _vp, c_int32, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
     "hl_amp_gather_pairs": (c_int32, [_vp, _vp, c_int64, _vp, _vp, _vp, c_int64, _vp]),
     "hl_amp_disc_input": (c_int32, [_vp, _vp, _vp, _vp, c_float, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
@@ -79,6 +90,9 @@ def _load():
     if lib.hl_sizeof_env_buffers() != ctypes.sizeof(HlEnvBuffers):
         raise ImportError(f"HlEnvBuffers layout mismatch: python {ctypes.sizeof(HlEnvBuffers)} vs "
                           f"library {lib.hl_sizeof_env_buffers()}")
+    if lib.hl_sizeof_transition() != ctypes.sizeof(HlTransition):
+        raise ImportError(f"HlTransition layout mismatch: python {ctypes.sizeof(HlTransition)} vs "
+                          f"library {lib.hl_sizeof_transition()}")
     return lib
 
 

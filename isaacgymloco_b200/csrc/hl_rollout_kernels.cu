@@ -123,3 +123,109 @@ extern "C" int hl_adv_normalize(float* advantages, const double* moments, int64_
   HL_CHECK_LAUNCH();
   return HL_OK;
 }
+
+
+// ============================================================================= record transition
+// Fused runner patch + process_env_step + add_transitions (see include/himloco_b200.h).  Pure
+// data movement: CTA = REC_TILE consecutive envs; every per-env tensor's rows of the tile are one
+// contiguous slab (128-bit copies, all loads of a thread issued before its stores); the
+// next-critic rows are copied per warp so a reset env can take its row from the terminal table
+// (row index = rank of the env id in the ascending id list, found by binary search).
+constexpr int REC_TILE = 32, REC_THREADS = 256;
+
+__device__ __forceinline__ void rec_copy_slab(float* __restrict__ dst, const float* __restrict__ src, long long off, int count,
+                                              int tid) {
+  if (!dst || !src) return;
+  dst += off;
+  src += off;
+  if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+    const int n4 = count >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    int i = tid;
+    for (; i + 3 * REC_THREADS < n4; i += 4 * REC_THREADS) {  // 4 x 16 B in flight per thread
+      const float4 a = __ldcs(s4 + i), b = __ldcs(s4 + i + REC_THREADS), c = __ldcs(s4 + i + 2 * REC_THREADS),
+                   d = __ldcs(s4 + i + 3 * REC_THREADS);
+      __stcs(d4 + i, a);
+      __stcs(d4 + i + REC_THREADS, b);
+      __stcs(d4 + i + 2 * REC_THREADS, c);
+      __stcs(d4 + i + 3 * REC_THREADS, d);
+    }
+    for (; i < n4; i += REC_THREADS) __stcs(d4 + i, __ldcs(s4 + i));
+    for (int k = (n4 << 2) + tid; k < count; k += REC_THREADS) dst[k] = src[k];
+  } else {
+    for (int k = tid; k < count; k += REC_THREADS) dst[k] = src[k];
+  }
+}
+
+__global__ void __launch_bounds__(REC_THREADS) hl_record_transition_kernel(HlTransition t, long long n) {
+  hl_pdl_enter();
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long e0 = (long long)blockIdx.x * REC_TILE;
+  const int cnt = (int)((n - e0) < REC_TILE ? (n - e0) : REC_TILE);
+  // per-env scalars first (their loads overlap the slab copies)
+  if (tid < cnt) {
+    const long long e = e0 + tid;
+    if (t.rewards && t.rewards_out) {
+      float r = t.rewards[e];
+      if (t.time_outs) r = __fadd_rn(r, __fmul_rn(t.gamma, __fmul_rn(t.values[e], t.time_outs[e] ? 1.0f : 0.0f)));
+      t.rewards_out[e] = r;
+    }
+    if (t.dones && t.dones_out) t.dones_out[e] = t.dones[e] ? 1 : 0;
+    if (t.values && t.values_out) t.values_out[e] = t.values[e];
+    if (t.log_prob && t.log_prob_out) t.log_prob_out[e] = t.log_prob[e];
+  }
+  rec_copy_slab(t.obs_out, t.obs, e0 * t.obs_dim, cnt * t.obs_dim, tid);
+  rec_copy_slab(t.critic_out, t.critic_obs, e0 * t.priv_dim, cnt * t.priv_dim, tid);
+  rec_copy_slab(t.actions_out, t.actions, e0 * t.act_dim, cnt * t.act_dim, tid);
+  rec_copy_slab(t.mu_out, t.mu, e0 * t.act_dim, cnt * t.act_dim, tid);
+  rec_copy_slab(t.sigma_out, t.sigma, e0 * t.act_dim, cnt * t.act_dim, tid);
+  if (t.next_critic_obs && t.next_critic_out) {
+    if (!t.term_ids) {
+      rec_copy_slab(t.next_critic_out, t.next_critic_obs, e0 * t.priv_dim, cnt * t.priv_dim, tid);
+    } else {
+      const int n_term = *t.n_term_dev;
+      const int PD = t.priv_dim;
+      for (int r = wid; r < cnt; r += REC_THREADS / 32) {
+        const long long e = e0 + r;
+        // lower_bound(term_ids, e): warp-uniform binary search
+        int lo = 0, hi = n_term;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (t.term_ids[mid] < e) lo = mid + 1;
+          else hi = mid;
+        }
+        const bool hit = lo < n_term && t.term_ids[lo] == e;
+        const float* src = hit ? t.term_rows + (long long)lo * PD : t.next_critic_obs + e * PD;
+        float* dst = t.next_critic_out + e * PD;
+        if (((PD & 1) == 0) && ((((uintptr_t)src | (uintptr_t)dst) & 7) == 0)) {
+          const float2* s2 = reinterpret_cast<const float2*>(src);
+          float2* d2 = reinterpret_cast<float2*>(dst);
+          const int n2 = PD >> 1;
+          float2 v[4];
+          for (int i0 = 0; i0 < n2; i0 += 128) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (i0 + u * 32 + lane < n2) ? __ldcs(s2 + i0 + u * 32 + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (i0 + u * 32 + lane < n2) __stcs(d2 + i0 + u * 32 + lane, v[u]);
+          }
+        } else {
+          for (int i = lane; i < PD; i += 32) dst[i] = src[i];
+        }
+      }
+    }
+  }
+}
+
+extern "C" int hl_sizeof_transition(void) { return (int)sizeof(HlTransition); }
+extern "C" int hl_record_transition(const HlTransition* t, int64_t n, void* stream) {
+  HL_CHECK_ARG(t && t->struct_bytes == (int)sizeof(HlTransition), "HlTransition size mismatch (ABI)");
+  HL_CHECK_ARG(t->obs_dim > 0 && t->priv_dim > 0 && t->act_dim > 0, "bad dims");
+  HL_CHECK_ARG(!t->term_ids || (t->n_term_dev && t->term_rows), "term_ids needs n_term_dev and term_rows");
+  HL_CHECK_ARG(!t->time_outs || t->values, "the time-out bootstrap needs values");
+  if (n <= 0) return HL_OK;
+  hl_launch(hl_record_transition_kernel, dim3((unsigned)((n + REC_TILE - 1) / REC_TILE)), dim3(REC_THREADS), 0, (cudaStream_t)stream, *t,
+            (long long)n);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}

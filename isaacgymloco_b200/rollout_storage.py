@@ -56,23 +56,98 @@ class HIMRolloutStorage:
         self.shard_statistics = bool(shard_statistics)
         self.process_group = process_group
 
-    def add_transitions(self, transition):
+    # ------------------------------------------------------------------ recording one env step
+    def _rows(self, x, width, dtype=torch.float32):
+        """(N,width) contiguous device rows of `x` (no copy when it already is)."""
+        x = x.detach()
+        if dtype == torch.uint8:
+            if x.dtype == torch.bool:
+                x = x.view(torch.uint8) if x.is_contiguous() else x.to(torch.uint8)
+            elif x.dtype != torch.uint8:
+                x = (x != 0).to(torch.uint8)
+        elif x.dtype != dtype:
+            x = x.to(dtype)
+        if x.device != self.device:
+            x = x.to(self.device)
+        x = x.reshape(self.num_envs, width)
+        return x if x.is_contiguous() else x.contiguous()
+
+    def _record(self, tr, rewards, dones, time_outs, next_critic, term_ids, term_rows, gamma, term_count=None,
+                assume_sorted=True):
         if self.step >= self.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
-        s = self.step
-        self.observations[s].copy_(transition.observations)
-        if self.privileged_observations is not None:
-            self.privileged_observations[s].copy_(transition.critic_observations)
-        if self.next_privileged_observations is not None:
-            self.next_privileged_observations[s].copy_(transition.next_critic_observations)
-        self.actions[s].copy_(transition.actions)
-        self.rewards[s].copy_(transition.rewards.view(-1, 1))
-        self.dones[s].copy_(transition.dones.view(-1, 1))
-        self.values[s].copy_(transition.values)
-        self.actions_log_prob[s].copy_(transition.actions_log_prob.view(-1, 1))
-        self.mu[s].copy_(transition.action_mean)
-        self.sigma[s].copy_(transition.action_sigma)
+        s, n = self.step, self.num_envs
+        od = self.observations.shape[-1]
+        ad = self.actions.shape[-1]
+        has_priv = self.privileged_observations is not None
+        pd = self.privileged_observations.shape[-1] if has_priv else 1
+        keep = []   # sources must outlive the enqueue
+
+        def src(x, width, dtype=torch.float32):
+            r = self._rows(x, width, dtype)
+            keep.append(r)
+            return r
+
+        def pair(x, slot, width, dtype=torch.float32):
+            """(src_ptr, dst_ptr); an in-place source (the env wrote the slot already) is skipped."""
+            if x is None or slot is None:
+                return None, None
+            r = src(x, width, dtype)
+            if r.data_ptr() == slot.data_ptr():
+                return None, None
+            return L.ptr(r), L.ptr(slot)
+
+        t = L.HlTransition()
+        t.struct_bytes = L.ctypes.sizeof(L.HlTransition)
+        t.obs_dim, t.priv_dim, t.act_dim, t.gamma = od, pd, ad, float(gamma)
+        t.obs, t.obs_out = pair(tr.observations, self.observations[s], od)
+        if has_priv:
+            t.critic_obs, t.critic_out = pair(tr.critic_observations, self.privileged_observations[s], pd)
+            t.next_critic_obs, t.next_critic_out = pair(next_critic, self.next_privileged_observations[s], pd)
+            if term_ids is not None and t.next_critic_out:
+                ids = term_ids.detach().to(self.device, torch.int64).flatten().contiguous()
+                rows = term_rows.detach().to(self.device, torch.float32).reshape(-1, pd).contiguous()
+                if not assume_sorted:      # reset_buf.nonzero() is ascending; other id lists are sorted here (no host sync)
+                    ids, order = torch.sort(ids, stable=True)
+                    rows = rows[order]
+                if term_count is not None:  # device-side count of over-allocated id/row buffers (sync-free env.step)
+                    cnt = term_count.detach().to(self.device, torch.int32).reshape(1)
+                else:
+                    cnt = torch.full((1,), ids.numel(), dtype=torch.int32, device=self.device)
+                keep.extend([ids, rows, cnt])
+                if ids.numel() > 0:
+                    t.term_ids, t.n_term_dev, t.term_rows = L.ptr(ids), L.ptr(cnt), L.ptr(rows)
+        t.actions, t.actions_out = pair(tr.actions, self.actions[s], ad)
+        t.rewards, t.rewards_out = pair(rewards, self.rewards[s], 1)
+        t.dones, t.dones_out = pair(dones, self.dones[s], 1, torch.uint8)
+        t.values, t.values_out = pair(tr.values, self.values[s], 1)
+        if time_outs is not None:
+            t.time_outs = L.ptr(src(time_outs, 1, torch.uint8))
+            if not t.values:
+                t.values = L.ptr(src(tr.values, 1))
+        t.log_prob, t.log_prob_out = pair(tr.actions_log_prob, self.actions_log_prob[s], 1)
+        t.mu, t.mu_out = pair(tr.action_mean, self.mu[s], ad)
+        t.sigma, t.sigma_out = pair(tr.action_sigma, self.sigma[s], ad)
+        L.check(L.lib.hl_record_transition(L.ctypes.byref(t), n, L.stream()))
         self.step += 1
+
+    def add_transitions(self, transition):
+        """him_rollout_storage.py:92-108: the ten slot copies of one step, as ONE launch."""
+        self._record(transition, transition.rewards, transition.dones, None, transition.next_critic_observations,
+                     None, None, 0.0)
+
+    def record_env_step(self, transition, rewards, dones, infos, privileged_obs, termination_ids,
+                        termination_privileged_obs, gamma, termination_count=None, assume_sorted=True):
+        """The runner's terminal-observation patch (him_on_policy_runner.py:122-123),
+        HIMPPO.process_env_step's time-out bootstrap (him_ppo.py:104-115) and add_transitions, fused:
+        `privileged_obs` is the env's post-step privileged observation, un-patched; nothing is
+        cloned.  `transition` carries what HIMPPO.act stored (observations, critic_observations,
+        actions, values, actions_log_prob, action_mean, action_sigma).  `termination_ids` must be
+        ascending (reset_buf.nonzero() is) unless assume_sorted=False; with `termination_count` (a
+        device int32 scalar) the id / row buffers may be over-allocated and no host sync happens."""
+        time_outs = infos.get("time_outs") if infos is not None else None
+        self._record(transition, rewards, dones, time_outs, privileged_obs, termination_ids, termination_privileged_obs,
+                     gamma, termination_count, assume_sorted)
 
     def clear(self):
         self.step = 0

@@ -28,3 +28,10 @@ def per_env_step_bytes(cfg: HotPathCfg, rollout_len: int = 24):
     gae = (4 + 4 + 1) + (4 + 4) + (4 + 4)                       # scan reads, scan writes, normalise r/w
     return dict(post_physics=post, post_physics_read=sum(reads.values()), post_physics_write=sum(writes.values()),
                 pd_torque=pd, gae=gae, total=post + pd + gae)
+
+
+def record_transition_bytes(obs_dim: int = 270, priv_dim: int = 238, act_dim: int = 12):
+    """hl_record_transition: every field is read once and written once."""
+    reads = 4 * (obs_dim + 2 * priv_dim + 3 * act_dim) + 4 + 1 + 4 + 1 + 4     # + rewards, dones, values, time_outs, log_prob
+    writes = 4 * (obs_dim + 2 * priv_dim + 3 * act_dim) + 4 + 1 + 4 + 4
+    return dict(read=reads, write=writes, total=reads + writes)

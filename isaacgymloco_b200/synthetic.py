@@ -240,5 +240,22 @@ def make_rollout(n: int, t: int, seed: int = 1234) -> Dict[str, torch.Tensor]:
                 last_values=torch.randn(n, 1, generator=g))
 
 
+def make_transition(n: int, seed: int = 0, obs_dim: int = 270, priv_dim: int = 238, act_dim: int = 12,
+                    reset_frac: float = 0.02, timeout_frac: float = 0.5) -> Dict[str, torch.Tensor]:
+    """One synthetic rollout step as the runner sees it after env.step (CPU tensors): the policy's
+    transition fields, the env outputs, the reset id list and its terminal rows."""
+    g = torch.Generator().manual_seed(9176 + seed)
+    randn = lambda *s: torch.randn(*s, generator=g)
+    dones = torch.rand(n, generator=g) < reset_frac
+    ids = dones.nonzero(as_tuple=False).flatten()
+    time_outs = dones & (torch.rand(n, generator=g) < timeout_frac)
+    return {
+        "obs": randn(n, obs_dim), "critic_obs": randn(n, priv_dim), "privileged_obs": randn(n, priv_dim),
+        "termination_ids": ids, "termination_privileged_obs": randn(len(ids), priv_dim),
+        "actions": randn(n, act_dim), "rewards": 0.05 * randn(n), "dones": dones, "values": randn(n, 1),
+        "time_outs": time_outs, "log_prob": randn(n), "mu": randn(n, act_dim), "sigma": randn(n, act_dim).abs() + 0.1,
+    }
+
+
 def to_device(d: Dict[str, torch.Tensor], device) -> Dict[str, torch.Tensor]:
     return {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in d.items()}

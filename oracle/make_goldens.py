@@ -193,6 +193,43 @@ def mint_gae():
     print("[golden] gae")
 
 
+def mint_record():
+    """Rollout-step recording through the reference's own classes:
+    HIMPPO.process_env_step (him_ppo.py:104-115) on a real HIMRolloutStorage; the runner's
+    two-line terminal patch (him_on_policy_runner.py:122-123) is applied as the runner does."""
+    H.install_stubs()
+    from rsl_rl.storage import HIMRolloutStorage
+    from rsl_rl.algorithms import HIMPPO
+
+    class _AC:
+        def reset(self, dones=None):
+            pass
+
+    out = {}
+    for name, n, t, seed, gamma in (("a", 40, 2, 41, 0.99), ("b", 67, 2, 42, 0.99), ("one", 1, 2, 43, 0.9)):
+        alg = HIMPPO.__new__(HIMPPO)
+        alg.device, alg.gamma, alg.actor_critic = "cpu", gamma, _AC()
+        alg.transition = HIMRolloutStorage.Transition()
+        alg.storage = HIMRolloutStorage(n, t, [270], [238], [12], device="cpu")
+        for step in range(t):
+            tr = S.make_transition(n, seed * 10 + step, reset_frac=(1.0 if name == "one" and step == 1 else 0.05))
+            # HIMPPO.act (him_ppo.py:90-102) stores these on the transition
+            alg.transition.actions, alg.transition.values = tr["actions"], tr["values"]
+            alg.transition.actions_log_prob, alg.transition.action_mean = tr["log_prob"], tr["mu"]
+            alg.transition.action_sigma = tr["sigma"]
+            alg.transition.observations, alg.transition.critic_observations = tr["obs"], tr["critic_obs"]
+            next_critic_obs = tr["privileged_obs"].clone().detach()
+            next_critic_obs[tr["termination_ids"]] = tr["termination_privileged_obs"].clone().detach()
+            alg.process_env_step(tr["rewards"], tr["dones"], {"time_outs": tr["time_outs"]}, next_critic_obs)
+        st = alg.storage
+        for f in ("observations", "privileged_observations", "next_privileged_observations", "actions", "rewards", "dones",
+                  "values", "actions_log_prob", "mu", "sigma"):
+            out[f"{name}_{f}"] = getattr(st, f).numpy().copy()
+        out[f"{name}_meta"] = np.array([n, t, seed, gamma], dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "record.npz"), **out)
+    print("[golden] record")
+
+
 def mint_amp():
     H.install_stubs()
     np.random.seed(31)
@@ -267,6 +304,7 @@ def main():
     for case in ENV_CASES:
         mint_env_case(case)
     mint_gae()
+    mint_record()
     mint_amp()
 
 

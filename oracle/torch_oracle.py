@@ -580,6 +580,32 @@ def compute_returns(rewards, values, dones, last_values, gamma, lam):
     return returns, a
 
 
+# --------------------------------------------------------------------------- f1: record one rollout step
+def record_env_step(storage, step, tr, gamma):
+    """Runner patch + process_env_step + add_transitions for slot `step`:
+    rsl_rl/rsl_rl/runners/him_on_policy_runner.py:122-123,
+    rsl_rl/rsl_rl/algorithms/him_ppo.py:104-115,
+    rsl_rl/rsl_rl/storage/him_rollout_storage.py:92-108.
+    `storage`: dict of (T,N,.) tensors; `tr`: dict with obs, critic_obs, privileged_obs (after the
+    env step), termination_ids, termination_privileged_obs, actions, rewards, dones, values,
+    time_outs (or None), log_prob, mu, sigma."""
+    nxt = tr["privileged_obs"].clone()
+    nxt[tr["termination_ids"]] = tr["termination_privileged_obs"].clone()
+    rewards = tr["rewards"].clone()
+    if tr.get("time_outs") is not None:
+        rewards += gamma * torch.squeeze(tr["values"] * tr["time_outs"].unsqueeze(1), 1)
+    storage["observations"][step].copy_(tr["obs"])
+    storage["privileged_observations"][step].copy_(tr["critic_obs"])
+    storage["next_privileged_observations"][step].copy_(nxt)
+    storage["actions"][step].copy_(tr["actions"])
+    storage["rewards"][step].copy_(rewards.view(-1, 1))
+    storage["dones"][step].copy_(tr["dones"].view(-1, 1))
+    storage["values"][step].copy_(tr["values"])
+    storage["actions_log_prob"][step].copy_(tr["log_prob"].view(-1, 1))
+    storage["mu"][step].copy_(tr["mu"])
+    storage["sigma"][step].copy_(tr["sigma"])
+
+
 # --------------------------------------------------------------------------- a16-a19: AMP
 _EPS = np.finfo(float).eps * 4.0        # rsl_rl/rsl_rl/utils/utils.py:35
 

@@ -89,6 +89,113 @@ def _loader(gold, preload=False, n_pre=0):
     return AMPLoader("cuda:0", 0.02, preload_transitions=preload, num_preload_transitions=n_pre, clip_tables=tables)
 
 
+# ----------------------------------------------------------------------------- rollout-step recording (§8f rank 1)
+def _transition(tr, dev="cuda:0"):
+    from isaacgymloco_b200.rollout_storage import HIMRolloutStorage
+    t = HIMRolloutStorage.Transition()
+    t.observations, t.critic_observations = tr["obs"].to(dev), tr["critic_obs"].to(dev)
+    t.actions, t.values, t.actions_log_prob = tr["actions"].to(dev), tr["values"].to(dev), tr["log_prob"].to(dev)
+    t.action_mean, t.action_sigma = tr["mu"].to(dev), tr["sigma"].to(dev)
+    return t
+
+
+def _record(st, tr, gamma, dev="cuda:0", **kw):
+    st.record_env_step(_transition(tr, dev), tr["rewards"].to(dev), tr["dones"].to(dev), {"time_outs": tr["time_outs"].to(dev)},
+                       tr["privileged_obs"].to(dev), tr["termination_ids"].to(dev),
+                       tr["termination_privileged_obs"].to(dev), gamma, **kw)
+
+
+@pytest.mark.parametrize("name", ["a", "b", "one"])
+def test_record_env_step_vs_reference_golden(name):
+    """hl_record_transition vs the reference's HIMPPO.process_env_step + add_transitions: bit-exact."""
+    from isaacgymloco_b200.rollout_storage import HIMRolloutStorage
+    from test_oracle_golden import RECORD_FIELDS, record_case_steps
+    gold = load_golden("record.npz")
+    n, t, seed, gamma = gold[f"{name}_meta"]
+    n, t = int(n), int(t)
+    st = HIMRolloutStorage(n, t, [270], [238], [12], device="cuda:0")
+    for tr in record_case_steps(name, n, t, int(seed)):
+        _record(st, tr, gamma)
+    assert st.step == t
+    for f in RECORD_FIELDS:
+        np.testing.assert_array_equal(getattr(st, f).cpu().numpy(), gold[f"{name}_{f}"], err_msg=f)
+    with pytest.raises(AssertionError, match="Rollout buffer overflow"):
+        _record(st, record_case_steps(name, n, 1, int(seed))[0], gamma)
+
+
+def test_record_env_step_full_size_and_variants():
+    """65,536 envs vs the oracle run on the same device; add_transitions drop-in (pre-patched
+    transition); over-allocated id buffers with a device-side count; unsorted ids; in-place slots."""
+    import oracle.torch_oracle as O
+    from isaacgymloco_b200 import synthetic as S
+    from isaacgymloco_b200.rollout_storage import HIMRolloutStorage
+    from test_oracle_golden import RECORD_FIELDS
+    n, t, gamma, dev = 65536, 2, 0.99, "cuda:0"
+    steps = [{k: v.to(dev) for k, v in S.make_transition(n, 70 + i).items()} for i in range(t)]
+    ref = {f: torch.zeros(t, n, {"observations": 270, "privileged_observations": 238, "next_privileged_observations": 238,
+                                  "actions": 12, "mu": 12, "sigma": 12}.get(f, 1), device=dev,
+                          dtype=torch.uint8 if f == "dones" else torch.float32) for f in RECORD_FIELDS}
+    for i, tr in enumerate(steps):
+        O.record_env_step(ref, i, tr, gamma)
+
+    def check(st, msg):
+        for f in RECORD_FIELDS:
+            assert torch.equal(getattr(st, f), ref[f]), f"{msg}: {f}"
+
+    # fused call
+    st = HIMRolloutStorage(n, t, [270], [238], [12], device=dev)
+    for tr in steps:
+        _record(st, tr, gamma)
+    check(st, "fused")
+    # drop-in add_transitions: the caller did the patch and the bootstrap (reference flow)
+    st = HIMRolloutStorage(n, t, [270], [238], [12], device=dev)
+    for tr in steps:
+        tt = _transition(tr)
+        nxt = tr["privileged_obs"].clone()
+        nxt[tr["termination_ids"]] = tr["termination_privileged_obs"]
+        tt.next_critic_observations = nxt
+        tt.rewards = tr["rewards"] + gamma * torch.squeeze(tr["values"] * tr["time_outs"].unsqueeze(1), 1)
+        tt.dones = tr["dones"]
+        st.add_transitions(tt)
+    check(st, "add_transitions")
+    # over-allocated id / row buffers + device-side count (what a sync-free env.step hands over)
+    st = HIMRolloutStorage(n, t, [270], [238], [12], device=dev)
+    for tr in steps:
+        k = tr["termination_ids"].numel()
+        ids = torch.full((n,), -1, dtype=torch.int64, device=dev)
+        ids[:k] = tr["termination_ids"]
+        rows = torch.full((k + 100, 238), float("nan"), device=dev)
+        rows[:k] = tr["termination_privileged_obs"]
+        st.record_env_step(_transition(tr), tr["rewards"], tr["dones"], {"time_outs": tr["time_outs"]}, tr["privileged_obs"],
+                           ids, rows, gamma, termination_count=torch.tensor([k], dtype=torch.int32, device=dev))
+    check(st, "device count")
+    # unsorted ids
+    st = HIMRolloutStorage(n, t, [270], [238], [12], device=dev)
+    for tr in steps:
+        perm = torch.randperm(tr["termination_ids"].numel(), device=dev)
+        tr2 = dict(tr, termination_ids=tr["termination_ids"][perm], termination_privileged_obs=tr["termination_privileged_obs"][perm])
+        _record(st, tr2, gamma, assume_sorted=False)
+    check(st, "unsorted")
+    # in-place: the env wrote obs / critic obs straight into the slot -> those copies are skipped
+    st = HIMRolloutStorage(n, t, [270], [238], [12], device=dev)
+    for i, tr in enumerate(steps):
+        st.observations[i].copy_(tr["obs"])
+        st.privileged_observations[i].copy_(tr["critic_obs"])
+        tt = _transition(tr)
+        tt.observations, tt.critic_observations = st.observations[i], st.privileged_observations[i]
+        st.record_env_step(tt, tr["rewards"], tr["dones"], {"time_outs": tr["time_outs"]}, tr["privileged_obs"],
+                           tr["termination_ids"], tr["termination_privileged_obs"], gamma)
+    check(st, "in place")
+    # no resets, no time-out info, odd env count (ragged last tile)
+    n2 = 1000 + 7
+    tr = {k: v.to(dev) for k, v in S.make_transition(n2, 5, reset_frac=0.0).items()}
+    st = HIMRolloutStorage(n2, 1, [270], [238], [12], device=dev)
+    st.record_env_step(_transition(tr), tr["rewards"], tr["dones"], {}, tr["privileged_obs"], tr["termination_ids"],
+                       tr["termination_privileged_obs"], gamma)
+    assert torch.equal(st.next_privileged_observations[0], tr["privileged_obs"])
+    assert torch.equal(st.rewards[0, :, 0], tr["rewards"]) and torch.equal(st.observations[0], tr["obs"])
+
+
 def test_amp_frame_blend_vs_reference_golden():
     gold = load_golden("amp.npz")
     ld = _loader(gold)

@@ -54,6 +54,32 @@ def test_gae(name):
     np.testing.assert_array_equal(adv.numpy(), gold[f"{name}_advantages"])
 
 
+RECORD_FIELDS = ("observations", "privileged_observations", "next_privileged_observations", "actions", "rewards", "dones",
+                 "values", "actions_log_prob", "mu", "sigma")
+
+
+def record_case_steps(name, n, t, seed):
+    """The synthetic per-step inputs oracle/make_goldens.py::mint_record fed the reference."""
+    from isaacgymloco_b200 import synthetic as S
+    return [S.make_transition(n, seed * 10 + step, reset_frac=(1.0 if name == "one" and step == 1 else 0.05))
+            for step in range(t)]
+
+
+@pytest.mark.parametrize("name", ["a", "b", "one"])
+def test_record_env_step(name):
+    """Oracle restatement of runner patch + process_env_step + add_transitions vs the reference's
+    own HIMPPO / HIMRolloutStorage (bit-exact: copies plus one bootstrap expression)."""
+    gold = load_golden("record.npz")
+    n, t, seed, gamma = gold[f"{name}_meta"]
+    n, t = int(n), int(t)
+    st = {f: torch.zeros(gold[f"{name}_{f}"].shape, dtype=torch.uint8 if f == "dones" else torch.float32)
+          for f in RECORD_FIELDS}
+    for step, tr in enumerate(record_case_steps(name, n, t, int(seed))):
+        O.record_env_step(st, step, tr, gamma)
+    for f in RECORD_FIELDS:
+        np.testing.assert_array_equal(st[f].numpy(), gold[f"{name}_{f}"], err_msg=f)
+
+
 def _table(gold):
     clips = [torch.from_numpy(gold[f"clip{i}"]) for i in range(len(gold["frame_durations"]))]
     return O.OracleMotionTable(clips, gold["frame_durations"], gold["weights_raw"], 0.02)
