@@ -142,6 +142,7 @@ class FusedLeggedRobot:
         self._c = cfg.to_c()
         self._bufs = None
         self._fused_event_hook = None      # bench.py: CUDA-event pair around the fused kernel
+        self._rollout = None               # bind_rollout(): storage whose slots the env writes in place
         self._prepare_terrain()
 
     # ------------------------------------------------------------------ plumbing
@@ -164,6 +165,38 @@ class FusedLeggedRobot:
     def refresh_buffers(self):
         """Call after rebinding any tensor attribute (pointers are cached in a C struct)."""
         self._bufs = None
+
+    # ------------------------------------------------------------------ zero-copy rollout slots
+    def bind_rollout(self, storage):
+        """Make the env read its observation history from rollout slot `storage.step` and write the
+        new observations / privileged observations into slot step+1 of a
+        HIMRolloutStorage(env_writes_slots=True): add_transitions' two largest copies
+        (him_rollout_storage.py:97-98) disappear because transition.observations and
+        .critic_observations already ARE the slots.  bind_rollout(None) detaches."""
+        if storage is None:
+            if getattr(self, "_rollout", None) is not None:
+                self.obs_buf, self.privileged_obs_buf = self.obs_buf.clone(), self.privileged_obs_buf.clone()
+            self._rollout = None
+            self._bufs = None
+            return
+        if not getattr(storage, "env_writes_slots", False):
+            raise ValueError("bind_rollout needs HIMRolloutStorage(env_writes_slots=True)")
+        s = storage.step
+        storage.obs_slot(s).copy_(self.obs_buf)
+        storage.priv_slot(s).copy_(self.privileged_obs_buf)
+        self.obs_buf, self.privileged_obs_buf = storage.obs_slot(s), storage.priv_slot(s)
+        self._rollout = storage
+        self._bufs = None
+
+    def _bind_rollout_slot(self, bufs):
+        st = self._rollout
+        s = st.step
+        if s >= st.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")     # as add_transitions would (him_rollout_storage.py:94)
+        self.obs_buf, self.privileged_obs_buf = st.obs_slot(s + 1), st.priv_slot(s + 1)
+        bufs.obs_buf_in = L.ptr(st.obs_slot(s))
+        bufs.obs_buf_out = L.ptr(self.obs_buf)
+        bufs.privileged_obs_buf = L.ptr(self.privileged_obs_buf)
 
     def _buffers(self) -> L.HlEnvBuffers:
         if self._bufs is not None:
@@ -297,6 +330,8 @@ class FusedLeggedRobot:
     def fused_pre_reset(self):
         """Launch the fused kernel, the id compaction and the terminal rows; no host sync."""
         bufs = self._buffers()
+        if getattr(self, "_rollout", None) is not None:
+            self._bind_rollout_slot(bufs)
         c, b = ctypes.byref(self._c), ctypes.byref(bufs)
         ev = self._fused_event_hook() if self._fused_event_hook is not None else None
         L.check(L.lib.hl_post_physics_fused(c, b, self.num_envs, L.stream()))

@@ -29,16 +29,22 @@ class HIMRolloutStorage:
             self.__init__()
 
     def __init__(self, num_envs, num_transitions_per_env, obs_shape, privileged_obs_shape, actions_shape,
-                 device="cuda:0", shard_statistics=False, process_group=None):
+                 device="cuda:0", shard_statistics=False, process_group=None, env_writes_slots=False):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("HIMRolloutStorage (B200) runs on CUDA only (no CPU fallback)")
         self.obs_shape, self.privileged_obs_shape, self.actions_shape = obs_shape, privileged_obs_shape, actions_shape
         t, n, dev = num_transitions_per_env, num_envs, self.device
         z = lambda *s: torch.zeros(t, n, *s, device=dev)
-        self.observations = z(*obs_shape)
+        # env_writes_slots: one extra slot so FusedLeggedRobot.bind_rollout() can make the env write
+        # its observations straight into slot step+1 (slot T carries over into slot 0 at clear())
+        self.env_writes_slots = bool(env_writes_slots)
+        extra = 1 if self.env_writes_slots else 0
+        self._obs_all = torch.zeros(t + extra, n, *obs_shape, device=dev)
+        self.observations = self._obs_all[:t]
         if privileged_obs_shape[0] is not None:
-            self.privileged_observations = z(*privileged_obs_shape)
+            self._priv_all = torch.zeros(t + extra, n, *privileged_obs_shape, device=dev)
+            self.privileged_observations = self._priv_all[:t]
             self.next_privileged_observations = z(*privileged_obs_shape)
         else:
             self.privileged_observations = None
@@ -150,7 +156,20 @@ class HIMRolloutStorage:
                      gamma, termination_count, assume_sorted)
 
     def clear(self):
+        if self.env_writes_slots and self.step == self.num_transitions_per_env:
+            # the observation the last env step produced opens the next rollout
+            self._obs_all[0].copy_(self._obs_all[self.step])
+            if self.privileged_observations is not None:
+                self._priv_all[0].copy_(self._priv_all[self.step])
         self.step = 0
+
+    def obs_slot(self, i):
+        """(N,obs) slot i in [0, T] (env_writes_slots=True only): where the env reads (i = step) and
+        writes (i = step+1) its observation history."""
+        return self._obs_all[i]
+
+    def priv_slot(self, i):
+        return self._priv_all[i]
 
     def compute_returns(self, last_values, gamma, lam):
         """him_rollout_storage.py:113-127: reverse-time GAE scan, then global advantage

@@ -328,3 +328,50 @@ def test_generic_grid_and_clipped_heights_path():
         assert_equal(ids, oids, "env_ids")
         assert_close(term_obs, oterm, "termination_privileged_obs")
         compare_snapshots(env.snapshot(), oenv.snapshot())
+
+
+def test_env_writes_rollout_slots_in_place():
+    """bind_rollout(): the env reads its history from rollout slot `step` and writes observations /
+    privileged observations into slot step+1, so record_env_step skips those two copies.  Three
+    steps of a bound env + storage must equal an unbound env whose outputs are recorded by copy."""
+    from gpu_helpers import make_env
+    from isaacgymloco_b200 import config as C, synthetic as S
+    from isaacgymloco_b200.rollout_storage import HIMRolloutStorage
+    n, t, gamma, dev = 4096, 3, 0.99, "cuda:0"
+    cfg = C.aliengo("flat", num_envs=n)
+    hf = S.make_terrain(cfg, seed=5)
+    state = S.make_state(cfg, n, hf, seed=91)
+    targets = S.make_reset_targets(cfg, state, hf, seed=92)
+    envs = [make_env(cfg, state, hf, targets, S.make_noise(n, seed=93)) for _ in range(2)]
+    stores = [HIMRolloutStorage(n, t, [270], [envs[0].num_privileged_obs], [12], device=dev, env_writes_slots=w) for w in (False, True)]
+    envs[1].bind_rollout(stores[1])
+    with pytest.raises(ValueError):
+        envs[0].bind_rollout(stores[0])
+    pol = [{k: v.to(dev) for k, v in S.make_transition(n, 200 + i, priv_dim=envs[0].num_privileged_obs).items()} for i in range(t)]
+    for i in range(t):
+        for env, st in zip(envs, stores):
+            tt = HIMRolloutStorage.Transition()
+            tt.observations, tt.critic_observations = env.obs_buf, env.privileged_obs_buf
+            if st.env_writes_slots:
+                assert tt.observations.data_ptr() == st.observations[i].data_ptr()
+            else:
+                tt.observations, tt.critic_observations = tt.observations.clone(), tt.critic_observations.clone()
+            tt.actions, tt.values, tt.actions_log_prob = pol[i]["actions"], pol[i]["values"], pol[i]["log_prob"]
+            tt.action_mean, tt.action_sigma = pol[i]["mu"], pol[i]["sigma"]
+            obs, priv, rew, dones, extras, ids, term_priv = env.step(tt.actions)
+            st.record_env_step(tt, rew, dones, {"time_outs": env.time_out_buf}, priv, ids, term_priv, gamma)
+    for f in ("observations", "privileged_observations", "next_privileged_observations", "actions", "rewards", "dones",
+              "values", "actions_log_prob", "mu", "sigma"):
+        assert torch.equal(getattr(stores[0], f), getattr(stores[1], f)), f
+    assert torch.equal(envs[0].obs_buf, envs[1].obs_buf) and torch.equal(envs[0].privileged_obs_buf, envs[1].privileged_obs_buf)
+    assert stores[0].dones.sum() > 0
+    with pytest.raises(AssertionError, match="Rollout buffer overflow"):
+        envs[1].step(pol[0]["actions"])
+    # next rollout: slot T carries over into slot 0
+    last = envs[1].obs_buf.clone()
+    stores[1].clear()
+    assert torch.equal(stores[1].observations[0], last)
+    envs[1].step(pol[0]["actions"])
+    assert envs[1].obs_buf.data_ptr() == stores[1].obs_slot(1).data_ptr()
+    envs[1].bind_rollout(None)
+    assert envs[1].obs_buf.data_ptr() != stores[1].obs_slot(1).data_ptr()
