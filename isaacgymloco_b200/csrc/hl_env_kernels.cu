@@ -1011,6 +1011,9 @@ struct FusedArgs {
 #define FK_NS fk52
 #define FK_EPB 52
 #define FK_SCALAR_WARPS 2
+#ifdef HL_EXP_T288
+#define FK_THREADS 288
+#endif
 #define FK_GENERIC 0
 #define FK_COMPACT 0
 #include "hl_fused_kernel.inc"
