@@ -335,7 +335,8 @@ def run_gpu_arm(args):
     if world == 1:
         if not args.no_latency:
             line["latency_4096"] = measure_latency_4096(args)
-            line["next_rows"] = {"record_transition": measure_record_transition(args, peak)}
+            line["next_rows"] = {"record_transition": measure_record_transition(args, peak),
+                                 "minibatch_gather": measure_minibatch_gather(args, peak)}
         if not args.no_cpu:
             fn, cores = cpu_rollout_runner(4096, args.rollout)
             fn()
@@ -428,6 +429,37 @@ def measure_record_transition(args, peak_gbs):
     gbs = bytes_env * n / (ms * 1e-3) / 1e9
     return {"envs": n, "us_per_step": 1e3 * ms, "bytes_per_env": bytes_env, "achieved_GBps": gbs, "peak_GBps": peak_gbs,
             "frac": gbs / peak_gbs, "note": "slots rotate over 4 steps: 1.65 GB working set per pass, larger than L2"}
+
+
+def measure_minibatch_gather(args, peak_gbs):
+    """one minibatch (T*N/4 random rows of all ten rollout fields) gathered by
+    one fused launch; 16,384 envs x 24 steps (configs[3] sizes), beside torch's ten index gathers."""
+    from isaacgymloco_b200.rollout_storage import HIMRolloutStorage
+    n, t_len, dev = 16384, 24, torch.device("cuda", torch.cuda.current_device())
+    st = HIMRolloutStorage(n, t_len, [270], [238], [12], device=dev)
+    for x in st._batch_fields():
+        x.normal_()
+    perm = torch.randperm(n * t_len, device=dev)
+    mb = n * t_len // 4
+    fields = st._batch_fields()
+    chunks = [perm[i * mb:(i + 1) * mb] for i in range(4)]
+
+    def fused():
+        for c in chunks:
+            st.gather_batch(c, fields)
+
+    def eager():
+        for c in chunks:
+            for x in fields:
+                x[c]
+    for _ in range(2):
+        fused(); eager()
+    ms = timed(fused, 5, False) / 5 / 4
+    ms_t = timed(eager, 5, False) / 5 / 4
+    row_bytes = 2 * 4 * sum(int(x[0].numel()) for x in fields) + 8
+    gbs = row_bytes * mb / (ms * 1e-3) / 1e9
+    return {"rows": mb, "us_per_minibatch": 1e3 * ms, "bytes_per_row": row_bytes, "achieved_GBps": gbs, "peak_GBps": peak_gbs,
+            "frac": gbs / peak_gbs, "torch_index_us_per_minibatch": 1e3 * ms_t}
 
 
 def measure_latency_4096(args):

@@ -291,6 +291,24 @@ typedef struct HlTransition {
 int hl_sizeof_transition(void);
 int hl_record_transition(const HlTransition* t, int64_t n_envs, void* stream);
 
+/* HIMRolloutStorage.mini_batch_generator's row gathers --
+ * rsl_rl/rsl_rl/storage/him_rollout_storage.py:137-177: for one minibatch, `x.flatten(0,1)[batch_idx]`
+ * of all ten rollout fields (observations, critic observations, actions, next critic observations,
+ * values, advantages, returns, log-probs, mu, sigma), as ONE launch: each index is read once and
+ * every field's row is copied to dst[row].  Fields: src (n_src_rows, width) row-major, dst
+ * (n_rows, width).  Out-of-range indices are an error the caller must not make (rows are skipped). */
+#define HL_MAX_GATHER_FIELDS 12
+typedef struct HlGatherFields {
+  int32_t struct_bytes;            /* sizeof(HlGatherFields): ABI guard */
+  int32_t n_fields;
+  const float* src[HL_MAX_GATHER_FIELDS];
+  float* dst[HL_MAX_GATHER_FIELDS];
+  int32_t width[HL_MAX_GATHER_FIELDS];
+} HlGatherFields;
+int hl_sizeof_gather_fields(void);
+int hl_minibatch_gather(const HlGatherFields* f, const int64_t* indices, int64_t n_rows, int64_t n_src_rows,
+                        void* stream);
+
 /* AMPLoader.get_full_frame_at_time_batch(traj_idxs, times) --
  * rsl_rl/rsl_rl/datasets/motion_loader.py:231-255 with quaternion_slerp
  * rsl_rl/rsl_rl/utils/utils.py:153-186.  `frames` = all clips stacked (sum n_i, 49);

@@ -40,6 +40,15 @@ class HlTransition(ctypes.Structure):
         "rewards_out", "dones_out", "values_out", "log_prob_out", "mu_out", "sigma_out")]
 
 
+MAX_GATHER_FIELDS = 12
+
+
+class HlGatherFields(ctypes.Structure):
+    """Mirror of `struct HlGatherFields`."""
+    _fields_ = [("struct_bytes", c_int32), ("n_fields", c_int32), ("src", _vp * MAX_GATHER_FIELDS),
+                ("dst", _vp * MAX_GATHER_FIELDS), ("width", c_int32 * MAX_GATHER_FIELDS)]
+
+
 # stage bits (include/himloco_b200.h)
 ST_COUNTERS, ST_FRAME, ST_CONTACTS, ST_HEADING, ST_HEIGHTS = 0x001, 0x002, 0x004, 0x008, 0x010
 ST_TERMINATION, ST_REWARD, ST_OBS, ST_OBS_NOSHIFT, ST_OBS_CLIP = 0x020, 0x040, 0x080, 0x100, 0x200
@@ -66,6 +75,8 @@ EXPORTS = {
     "hl_adv_normalize": (c_int32, [_vp, _vp, c_int64, _vp]),
     "hl_sizeof_transition": (c_int32, []),
     "hl_record_transition": (c_int32, [POINTER(HlTransition), c_int64, _vp]),
+    "hl_sizeof_gather_fields": (c_int32, []),
+    "hl_minibatch_gather": (c_int32, [POINTER(HlGatherFields), _vp, c_int64, c_int64, _vp]),
     "hl_amp_frame_blend": (c_int32, [_vp, _vp, _vp, _vp, c_int32, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
     "hl_amp_gather_pairs": (c_int32, [_vp, _vp, c_int64, _vp, _vp, _vp, c_int64, _vp]),
     "hl_amp_disc_input": (c_int32, [_vp, _vp, _vp, _vp, c_float, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
@@ -90,6 +101,8 @@ def _load():
     if lib.hl_sizeof_env_buffers() != ctypes.sizeof(HlEnvBuffers):
         raise ImportError(f"HlEnvBuffers layout mismatch: python {ctypes.sizeof(HlEnvBuffers)} vs "
                           f"library {lib.hl_sizeof_env_buffers()}")
+    if lib.hl_sizeof_gather_fields() != ctypes.sizeof(HlGatherFields):
+        raise ImportError("HlGatherFields layout mismatch")
     if lib.hl_sizeof_transition() != ctypes.sizeof(HlTransition):
         raise ImportError(f"HlTransition layout mismatch: python {ctypes.sizeof(HlTransition)} vs "
                           f"library {lib.hl_sizeof_transition()}")

@@ -229,3 +229,77 @@ extern "C" int hl_record_transition(const HlTransition* t, int64_t n, void* stre
   HL_CHECK_LAUNCH();
   return HL_OK;
 }
+
+
+// ============================================================================= minibatch gather
+// CTA = 32 minibatch rows, 8 warps x 4 rows.  A warp copies its rows field by field (64-bit
+// accesses when the row width is even: 270/238/12-float rows are 8-B aligned), all loads of a
+// row's field in flight before its stores; width-1 fields are copied by warp 0, one lane per row
+// (coalesced stores).
+constexpr int GA_ROWS = 32, GA_THREADS = 256;
+
+__global__ void __launch_bounds__(GA_THREADS) hl_minibatch_gather_kernel(HlGatherFields f, const long long* __restrict__ indices,
+                                                                        long long n_rows, long long n_src) {
+  hl_pdl_enter();
+  __shared__ long long s_idx[GA_ROWS];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long r0 = (long long)blockIdx.x * GA_ROWS;
+  if (tid < GA_ROWS) {
+    long long ix = -1;
+    if (r0 + tid < n_rows) {
+      ix = indices[r0 + tid];
+      if (ix < 0 || ix >= n_src) ix = -1;
+    }
+    s_idx[tid] = ix;
+  }
+  __syncthreads();
+  for (int k = 0; k < f.n_fields; ++k) {
+    const int w = f.width[k];
+    const float* __restrict__ src = f.src[k];
+    float* __restrict__ dst = f.dst[k];
+    if (w == 1) {
+      if (wid == 0) {
+        const long long ix = s_idx[lane];
+        if (ix >= 0) dst[r0 + lane] = __ldg(src + ix);
+      }
+      continue;
+    }
+    const bool v2 = ((w & 1) == 0) && ((((uintptr_t)src | (uintptr_t)dst) & 7) == 0);
+    for (int q = 0; q < GA_ROWS / 8; ++q) {
+      const int r = wid * (GA_ROWS / 8) + q;
+      const long long ix = s_idx[r];
+      if (ix < 0) continue;
+      const float* srow = src + ix * w;
+      float* drow = dst + (r0 + r) * w;
+      if (v2) {
+        const float2* s2 = reinterpret_cast<const float2*>(srow);
+        float2* d2 = reinterpret_cast<float2*>(drow);
+        const int n2 = w >> 1;
+        for (int i0 = 0; i0 < n2; i0 += 160) {
+          float2 v[5];
+#pragma unroll
+          for (int u = 0; u < 5; ++u) v[u] = (i0 + u * 32 + lane < n2) ? __ldg(s2 + i0 + u * 32 + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 5; ++u)
+            if (i0 + u * 32 + lane < n2) __stcs(d2 + i0 + u * 32 + lane, v[u]);
+        }
+      } else {
+        for (int i = lane; i < w; i += 32) drow[i] = __ldg(srow + i);
+      }
+    }
+  }
+}
+
+extern "C" int hl_sizeof_gather_fields(void) { return (int)sizeof(HlGatherFields); }
+extern "C" int hl_minibatch_gather(const HlGatherFields* f, const int64_t* indices, int64_t n_rows, int64_t n_src_rows,
+                                   void* stream) {
+  HL_CHECK_ARG(f && f->struct_bytes == (int)sizeof(HlGatherFields), "HlGatherFields size mismatch (ABI)");
+  HL_CHECK_ARG(f->n_fields > 0 && f->n_fields <= HL_MAX_GATHER_FIELDS, "bad field count");
+  HL_CHECK_ARG(indices, "null indices");
+  for (int k = 0; k < f->n_fields; ++k) HL_CHECK_ARG(f->src[k] && f->dst[k] && f->width[k] > 0, "null field / bad width");
+  if (n_rows <= 0) return HL_OK;
+  hl_launch(hl_minibatch_gather_kernel, dim3((unsigned)((n_rows + GA_ROWS - 1) / GA_ROWS)), dim3(GA_THREADS), 0, (cudaStream_t)stream,
+            *f, (const long long*)indices, (long long)n_rows, (long long)n_src_rows);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}

@@ -202,23 +202,47 @@ class HIMRolloutStorage:
         lengths = idx[1:] - idx[:-1]
         return lengths.float().mean(), self.rewards.mean()
 
-    def mini_batch_generator(self, num_mini_batches, num_epochs=8):
-        """him_rollout_storage.py:137-177 (torch index gathers; a fused multi-tensor gather is a
-        "next" row)."""
-        batch = self.num_envs * self.num_transitions_per_env
-        mb = batch // num_mini_batches
-        indices = torch.randperm(num_mini_batches * mb, requires_grad=False, device=self.device)
+    def _batch_fields(self):
+        """The ten (T*N, width) views in the reference's yield order (him_rollout_storage.py:176-177)."""
         flat = lambda x: x.flatten(0, 1)
         obs = flat(self.observations)
         critic = flat(self.privileged_observations) if self.privileged_observations is not None else obs
         next_critic = flat(self.next_privileged_observations) if self.next_privileged_observations is not None else obs
-        acts, vals, rets = flat(self.actions), flat(self.values), flat(self.returns)
-        logp, adv, mu, sigma = flat(self.actions_log_prob), flat(self.advantages), flat(self.mu), flat(self.sigma)
+        return [obs, critic, flat(self.actions), next_critic, flat(self.values), flat(self.advantages), flat(self.returns),
+                flat(self.actions_log_prob), flat(self.mu), flat(self.sigma)]
+
+    def gather_batch(self, batch_idx, fields=None):
+        """`x.flatten(0,1)[batch_idx]` of every rollout field as ONE launch (hl_minibatch_gather):
+        the index list is read once, each row of each field is copied once."""
+        fields = self._batch_fields() if fields is None else fields
+        idx = batch_idx.detach().to(self.device, torch.int64).contiguous()
+        m = idx.numel()
+        outs = [torch.empty((m,) + tuple(x.shape[1:]), device=self.device, dtype=torch.float32) for x in fields]
+        if m == 0:
+            return tuple(outs)
+        g = L.HlGatherFields()
+        g.struct_bytes = L.ctypes.sizeof(L.HlGatherFields)
+        g.n_fields = len(fields)
+        srcs = []
+        for k, (x, o) in enumerate(zip(fields, outs)):
+            x = x if (x.is_contiguous() and x.dtype == torch.float32) else x.contiguous().float()
+            srcs.append(x)
+            g.src[k], g.dst[k], g.width[k] = L.ptr(x), L.ptr(o), int(x[0].numel())
+        L.check(L.lib.hl_minibatch_gather(L.ctypes.byref(g), L.ptr(idx), m, int(fields[0].shape[0]), L.stream()))
+        return tuple(outs)
+
+    def mini_batch_generator(self, num_mini_batches, num_epochs=8, indices=None):
+        """him_rollout_storage.py:137-177: same permutation draw (torch.randperm on the device),
+        same slicing and yield order; the ten index gathers of a minibatch are one fused launch.
+        `indices` (optional) replaces the randperm draw (tests / replay)."""
+        batch = self.num_envs * self.num_transitions_per_env
+        mb = batch // num_mini_batches
+        if indices is None:
+            indices = torch.randperm(num_mini_batches * mb, requires_grad=False, device=self.device)
+        fields = self._batch_fields()
         for _ in range(num_epochs):
             for i in range(num_mini_batches):
-                ids = indices[i * mb:(i + 1) * mb]
-                yield (obs[ids], critic[ids], acts[ids], next_critic[ids], vals[ids], adv[ids], rets[ids], logp[ids],
-                       mu[ids], sigma[ids])
+                yield self.gather_batch(indices[i * mb:(i + 1) * mb], fields)
 
 
 RolloutStorage = HIMRolloutStorage

@@ -257,5 +257,14 @@ def make_transition(n: int, seed: int = 0, obs_dim: int = 270, priv_dim: int = 2
     }
 
 
+def make_filled_storage(n: int, t: int, seed: int = 0, obs_dim: int = 270, priv_dim: int = 238, act_dim: int = 12):
+    """Random contents for every (T,N,.) rollout field (CPU tensors, reference attribute names)."""
+    g = torch.Generator().manual_seed(5501 + seed)
+    r = lambda w: torch.randn(t, n, w, generator=g)
+    return {"observations": r(obs_dim), "privileged_observations": r(priv_dim), "next_privileged_observations": r(priv_dim),
+            "actions": r(act_dim), "values": r(1), "advantages": r(1), "returns": r(1), "actions_log_prob": r(1),
+            "mu": r(act_dim), "sigma": r(act_dim).abs()}
+
+
 def to_device(d: Dict[str, torch.Tensor], device) -> Dict[str, torch.Tensor]:
     return {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in d.items()}

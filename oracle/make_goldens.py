@@ -230,6 +230,27 @@ def mint_record():
     print("[golden] record")
 
 
+def mint_minibatch():
+    """mini_batch_generator of the reference's own HIMRolloutStorage on CPU; the
+    permutation it drew is recovered by re-seeding torch (same call, same generator state)."""
+    H.install_stubs()
+    from rsl_rl.storage import HIMRolloutStorage
+    n, t, nmb, epochs, seed = 6, 5, 2, 2, 77
+    st = HIMRolloutStorage(n, t, [270], [238], [12], device="cpu")
+    for k_, v in S.make_filled_storage(n, t, seed).items():
+        getattr(st, k_).copy_(v)
+    torch.manual_seed(seed)
+    batches = list(st.mini_batch_generator(nmb, epochs))
+    torch.manual_seed(seed)
+    indices = torch.randperm(nmb * ((n * t) // nmb))
+    out = {"meta": np.array([n, t, nmb, epochs, seed], dtype=np.int64), "indices": indices.numpy()}
+    for bi, b in enumerate(batches):
+        for fi, x in enumerate(b):
+            out[f"b{bi}_f{fi}"] = x.numpy().copy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "minibatch.npz"), **out)
+    print(f"[golden] minibatch: {len(batches)} batches")
+
+
 def mint_amp():
     H.install_stubs()
     np.random.seed(31)
@@ -305,6 +326,7 @@ def main():
         mint_env_case(case)
     mint_gae()
     mint_record()
+    mint_minibatch()
     mint_amp()
 
 

@@ -606,6 +606,23 @@ def record_env_step(storage, step, tr, gamma):
     storage["sigma"][step].copy_(tr["sigma"])
 
 
+# --------------------------------------------------------------------------- f3: minibatch gather
+MINIBATCH_ORDER = ("observations", "privileged_observations", "actions", "next_privileged_observations", "values",
+                   "advantages", "returns", "actions_log_prob", "mu", "sigma")
+
+
+def mini_batches(storage, num_mini_batches, num_epochs, indices):
+    """rsl_rl/rsl_rl/storage/him_rollout_storage.py:137-177 with the permutation given: yields the
+    ten `x.flatten(0,1)[batch_idx]` tensors in the reference's order."""
+    t, n = storage["observations"].shape[:2]
+    mb = (t * n) // num_mini_batches
+    flat = {k: storage[k].flatten(0, 1) for k in MINIBATCH_ORDER}
+    for _ in range(num_epochs):
+        for i in range(num_mini_batches):
+            idx = indices[i * mb:(i + 1) * mb]
+            yield tuple(flat[k][idx] for k in MINIBATCH_ORDER)
+
+
 # --------------------------------------------------------------------------- a16-a19: AMP
 _EPS = np.finfo(float).eps * 4.0        # rsl_rl/rsl_rl/utils/utils.py:35
 

@@ -196,6 +196,59 @@ def test_record_env_step_full_size_and_variants():
     assert torch.equal(st.rewards[0, :, 0], tr["rewards"]) and torch.equal(st.observations[0], tr["obs"])
 
 
+# ----------------------------------------------------------------------------- fused minibatch gather (§8f rank 3)
+def _filled(n, t, seed, dev="cuda:0"):
+    from isaacgymloco_b200 import synthetic as S
+    from isaacgymloco_b200.rollout_storage import HIMRolloutStorage
+    st = HIMRolloutStorage(n, t, [270], [238], [12], device=dev)
+    src = S.make_filled_storage(n, t, seed)
+    for k, v in src.items():
+        getattr(st, k).copy_(v)
+    return st, src
+
+
+def test_mini_batch_generator_vs_reference_golden():
+    """hl_minibatch_gather behind mini_batch_generator vs the reference generator: bit-exact rows,
+    same yield order and shapes."""
+    gold = load_golden("minibatch.npz")
+    n, t, nmb, epochs, seed = (int(x) for x in gold["meta"])
+    st, _ = _filled(n, t, seed)
+    batches = list(st.mini_batch_generator(nmb, epochs, indices=torch.from_numpy(gold["indices"]).cuda()))
+    assert len(batches) == nmb * epochs
+    for bi, b in enumerate(batches):
+        assert len(b) == 10
+        for fi, x in enumerate(b):
+            np.testing.assert_array_equal(x.cpu().numpy(), gold[f"b{bi}_f{fi}"], err_msg=f"batch {bi} field {fi}")
+
+
+def test_mini_batch_gather_full_size_properties():
+    """16,384 envs x 24 steps, 4 minibatches: every fused gather equals torch indexing; the
+    default (randperm) path yields each row exactly once per epoch; ragged / empty index lists."""
+    from oracle import torch_oracle as O
+    n, t, nmb = 16384, 24, 4
+    st, _ = _filled(n, t, 3)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    perm = torch.randperm(n * t, device="cuda", generator=g)
+    ref = {k: getattr(st, k) for k in O.MINIBATCH_ORDER}
+    for b, rb in zip(st.mini_batch_generator(nmb, 1, indices=perm), O.mini_batches(ref, nmb, 1, perm)):
+        for x, y in zip(b, rb):
+            assert x.shape == y.shape and torch.equal(x, y)
+    # default path: a permutation of all rows (checksum of the values column)
+    tot = torch.zeros((), dtype=torch.float64, device="cuda")
+    rows = 0
+    for b in st.mini_batch_generator(nmb, 1):
+        tot += b[4].double().sum()
+        rows += b[4].shape[0]
+    assert rows == n * t
+    assert abs(float(tot) - float(st.values.double().sum())) < 1e-6 * n * t
+    # ragged (not a multiple of the 32-row tile), duplicate and empty index lists
+    idx = torch.tensor([5, 5, n * t - 1, 0, 17] * 13, device="cuda")
+    out = st.gather_batch(idx)
+    for x, k in zip(out, O.MINIBATCH_ORDER):
+        assert torch.equal(x, getattr(st, k).flatten(0, 1)[idx])
+    assert st.gather_batch(idx[:0])[0].shape == (0, 270)
+
+
 def test_amp_frame_blend_vs_reference_golden():
     gold = load_golden("amp.npz")
     ld = _loader(gold)

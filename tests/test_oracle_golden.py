@@ -80,6 +80,19 @@ def test_record_env_step(name):
         np.testing.assert_array_equal(st[f].numpy(), gold[f"{name}_{f}"], err_msg=f)
 
 
+def test_mini_batch_generator():
+    """Oracle restatement of mini_batch_generator vs the reference's own generator (same permutation)."""
+    from isaacgymloco_b200 import synthetic as S
+    gold = load_golden("minibatch.npz")
+    n, t, nmb, epochs, seed = (int(x) for x in gold["meta"])
+    st = S.make_filled_storage(n, t, seed)
+    batches = list(O.mini_batches(st, nmb, epochs, torch.from_numpy(gold["indices"])))
+    assert len(batches) == nmb * epochs
+    for bi, b in enumerate(batches):
+        for fi, x in enumerate(b):
+            np.testing.assert_array_equal(x.numpy(), gold[f"b{bi}_f{fi}"], err_msg=f"batch {bi} field {fi}")
+
+
 def _table(gold):
     clips = [torch.from_numpy(gold[f"clip{i}"]) for i in range(len(gold["frame_durations"]))]
     return O.OracleMotionTable(clips, gold["frame_durations"], gold["weights_raw"], 0.02)
