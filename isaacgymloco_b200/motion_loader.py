@@ -68,6 +68,7 @@ class AMPLoader:
             weights.append(float(clip_tables["weights"][i]))
             lens.append((full.shape[0] - 1) * dur)             # ML:109 (count-1) * dt
             nframes.append(float(full.shape[0]))               # ML:111 the frame COUNT
+        self._raw_weights = np.array(weights, dtype=np.float64)
         self.trajectory_weights = np.array(weights) / np.sum(weights)
         self.trajectory_frame_durations = np.array(durations)
         self.trajectory_lens = np.array(lens)
@@ -84,6 +85,54 @@ class AMPLoader:
             times = self.traj_time_sample_batch(traj_idxs)
             self.preloaded_s = self.get_full_frame_at_time_batch(traj_idxs, times)
             self.preloaded_s_next = self.get_full_frame_at_time_batch(traj_idxs, times + self.time_between_frames)
+
+    # ------------------------------------------------------------------ binary clip cache
+    # The reference re-parses the JSON clips and normalises every quaternion in a Python loop at each
+    # start-up (ML:76-111).  The cache holds the already reordered / normalised / standardised float64
+    # frame tables plus FrameDuration, MotionWeight and names: one .npz, loaded without parsing.
+    CACHE_VERSION = 1
+
+    @classmethod
+    def build_cache(cls, motion_files, path):
+        """Host-only: parse `motion_files` like the loader does and write the binary cache."""
+        tabs = dict(frames=[], frame_durations=[], weights=[], names=[])
+        for f in motion_files:
+            data, dur, w = cls._parse_motion_file(f)
+            tabs["frames"].append(data)
+            tabs["frame_durations"].append(dur)
+            tabs["weights"].append(w)
+            tabs["names"].append(f.split(".")[0])
+        cls._write_cache(path, tabs)
+        return tabs
+
+    @classmethod
+    def _write_cache(cls, path, tabs):
+        out = {"version": np.int64(cls.CACHE_VERSION), "n_clips": np.int64(len(tabs["frames"])),
+               "frame_durations": np.asarray(tabs["frame_durations"], dtype=np.float64),
+               "weights": np.asarray(tabs["weights"], dtype=np.float64), "names": np.asarray([str(x) for x in tabs["names"]])}
+        for i, fr in enumerate(tabs["frames"]):
+            out[f"clip{i}"] = np.asarray(fr)
+        with open(path, "wb") as fh:
+            np.savez(fh, **out)
+
+    @classmethod
+    def read_cache(cls, path):
+        with np.load(path, allow_pickle=False) as z:
+            if int(z["version"]) != cls.CACHE_VERSION:
+                raise ValueError(f"mocap cache version {int(z['version'])} != {cls.CACHE_VERSION}")
+            k = int(z["n_clips"])
+            return dict(frames=[z[f"clip{i}"] for i in range(k)], frame_durations=list(z["frame_durations"]),
+                        weights=list(z["weights"]), names=[str(x) for x in z["names"]])
+
+    def save_cache(self, path):
+        """Write this loader's clip tables (fp32 on the device -> exact round trip)."""
+        self._write_cache(path, dict(frames=[t.cpu().numpy() for t in self.trajectories_full],
+                                     frame_durations=self.trajectory_frame_durations, weights=self._raw_weights,
+                                     names=self.trajectory_names))
+
+    @classmethod
+    def from_cache(cls, path, device, time_between_frames, **kw):
+        return cls(device, time_between_frames, clip_tables=cls.read_cache(path), **kw)
 
     # ------------------------------------------------------------------ load time (host)
     @classmethod

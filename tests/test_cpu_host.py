@@ -104,3 +104,27 @@ def test_mocap_parser_matches_reference_loader():
         data, dur, w = AMPLoader._parse_motion_file(os.path.join(d, str(name)))
         np.testing.assert_array_equal(data[:, :49].astype(np.float32), gold[f"clip{i}"])
         assert dur == gold["frame_durations"][i] and w == gold["weights_raw"][i]
+
+
+def test_mocap_binary_cache_round_trip(tmp_path):
+    """the binary clip cache holds exactly what the JSON parse produces."""
+    from isaacgymloco_b200.motion_loader import AMPLoader
+    gold = load_golden("amp.npz")
+    k = len(gold["frame_durations"])
+    tabs = dict(frames=[gold[f"clip{i}"].astype(np.float64) for i in range(k)], frame_durations=list(gold["frame_durations"]),
+                weights=list(gold["weights_raw"]), names=[str(x) for x in gold["clip_names"]])
+    path = str(tmp_path / "clips.npz")
+    AMPLoader._write_cache(path, tabs)
+    back = AMPLoader.read_cache(path)
+    assert back["names"] == tabs["names"]
+    np.testing.assert_array_equal(back["frame_durations"], tabs["frame_durations"])
+    np.testing.assert_array_equal(back["weights"], tabs["weights"])
+    for a, b in zip(back["frames"], tabs["frames"]):
+        np.testing.assert_array_equal(a, b)
+    d = "/root/reference/datasets/mocap_motions_aliengo"
+    if os.path.isdir(d):   # build container: straight from the reference's JSON clips
+        files = [os.path.join(d, str(n)) for n in gold["clip_names"]]
+        AMPLoader.build_cache(files, path)
+        back = AMPLoader.read_cache(path)
+        for i, fr in enumerate(back["frames"]):
+            np.testing.assert_array_equal(fr[:, :49].astype(np.float32), gold[f"clip{i}"])

@@ -266,6 +266,23 @@ def test_amp_frame_blend_vs_reference_golden():
     np.testing.assert_allclose(got[:, 3:7], want[:, 3:7], rtol=1e-5, atol=1e-6, equal_nan=True)
 
 
+def test_amp_loader_from_binary_cache(tmp_path):
+    """save_cache -> from_cache gives the same tables and the same blended frames."""
+    gold = load_golden("amp.npz")
+    a = _loader(gold)
+    path = str(tmp_path / "clips.npz")
+    a.save_cache(path)
+    from isaacgymloco_b200.motion_loader import AMPLoader
+    b = AMPLoader.from_cache(path, "cuda:0", 0.02)
+    assert b.trajectory_names == a.trajectory_names
+    np.testing.assert_array_equal(b.trajectory_weights, a.trajectory_weights)
+    np.testing.assert_array_equal(b.trajectory_lens, a.trajectory_lens)
+    assert torch.equal(a.all_trajectories_full, b.all_trajectories_full)
+    fa = a.get_full_frame_at_time_batch(gold["blend_idx"], gold["blend_times"])
+    fb = b.get_full_frame_at_time_batch(gold["blend_idx"], gold["blend_times"])
+    assert torch.equal(fa, fb)
+
+
 def test_amp_frame_blend_config4_size():
     """configs[3]: 16,384 samples per batch (and a 2e5-sample preload) vs the oracle."""
     from oracle import torch_oracle as O
