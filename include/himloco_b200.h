@@ -232,6 +232,14 @@ int hl_select_and_terminal(const HlCfg* cfg, const HlEnvBuffers* bufs, const flo
 int hl_post_reset_fixup(const HlCfg* cfg, const HlEnvBuffers* bufs, const int64_t* env_ids,
                         const int32_t* n_ids_dev, int32_t with_reset_zero, int64_t n_envs, void* stream);
 
+/* reset_idx's episode logging -- LR:346-350: for every reward row k,
+ *   means_out[k] = mean_{e in env_ids}( episode_sums[k][e] / clip(episode_length_buf[e], min=1) / dt )
+ * (one launch instead of 21 masked-mean chains; the id count stays on the device).  With
+ * zero_rows != 0 the rows of the listed envs are zeroed afterwards (`episode_sums[key][env_ids] = 0`). */
+int hl_episode_means(float* episode_sums, const int64_t* episode_length_buf, const int64_t* env_ids,
+                     const int32_t* n_ids_dev, int32_t n_rows, int64_t n_envs, float dt, int32_t zero_rows,
+                     float* means_out, void* stream);
+
 /* get_amp_observations() for all envs -- LR:406-416: (N,30) = dof_pos, base_lin_vel,
  * base_ang_vel, dof_vel. */
 int hl_amp_observations(const float* dof_state, const float* base_lin_vel, const float* base_ang_vel,

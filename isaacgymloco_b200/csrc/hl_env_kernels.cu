@@ -842,6 +842,47 @@ extern "C" int hl_select_and_terminal(const HlCfg* cfg, const HlEnvBuffers* bufs
   return HL_OK;
 }
 
+// ============================================================================= episode logging of reset_idx
+// One CTA per reward row; threads stride over the reset id list, float64 partials, block reduce.
+__global__ void __launch_bounds__(256) hl_episode_means_kernel(float* __restrict__ sums, const long long* __restrict__ ep_len,
+                                                               const long long* __restrict__ ids, const int* __restrict__ n_ids,
+                                                               long long n, float dt, int zero_rows, float* __restrict__ out) {
+  hl_pdl_enter();
+  __shared__ double part[8];
+  const int k = blockIdx.x, tid = threadIdx.x;
+  const int cnt = *n_ids;
+  float* row = sums + (long long)k * n;
+  double acc = 0.0;
+  for (int i = tid; i < cnt; i += 256) {
+    const long long e = ids[i];
+    if (e < 0 || e >= n) continue;
+    const long long len = ep_len[e] < 1 ? 1 : ep_len[e];
+    acc += (double)__fdiv_rn(__fdiv_rn(row[e], (float)len), dt);   // LR:349 op order, each division rounded
+    if (zero_rows) row[e] = 0.0f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((tid & 31) == 0) part[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    out[k] = cnt > 0 ? (float)(t / (double)cnt) : 0.0f;
+  }
+}
+
+extern "C" int hl_episode_means(float* episode_sums, const int64_t* episode_length_buf, const int64_t* env_ids,
+                                const int32_t* n_ids_dev, int32_t n_rows, int64_t n, float dt, int32_t zero_rows,
+                                float* means_out, void* stream) {
+  HL_CHECK_ARG(episode_sums && episode_length_buf && env_ids && n_ids_dev && means_out, "null pointer");
+  HL_CHECK_ARG(dt > 0.0f, "dt must be positive");
+  if (n_rows <= 0 || n <= 0) return HL_OK;
+  hl_launch(hl_episode_means_kernel, dim3((unsigned)n_rows), dim3(256), 0, (cudaStream_t)stream, episode_sums,
+            (const long long*)episode_length_buf, (const long long*)env_ids, n_ids_dev, (long long)n, dt, (int)zero_rows, means_out);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}
+
 // ============================================================================= a13: AMP observations
 __global__ void __launch_bounds__(256) hl_amp_obs_kernel(const float* __restrict__ dof, const float* __restrict__ blv,
                                                          const float* __restrict__ bav, float* __restrict__ out,

@@ -416,12 +416,15 @@ class FusedLeggedRobot:
         self.feet_air_time[env_ids] = 0.0
         self.reset_buf[env_ids] = True
         self.extras["episode"] = {}
-        lengths = torch.clip(self.episode_length_buf[env_ids], min=1)
-        if self.episode_sums:
-            means = torch.mean(self._episode_sums_buf[:len(self.episode_sums), env_ids] / lengths / self.dt, dim=1)
+        if self.episode_sums:   # LR:346-350 as one launch (means of every row over the reset ids, rows zeroed)
+            rows = self._episode_sums_buf.shape[0]
+            means = torch.empty(rows, device=self.device)
+            ids = env_ids.to(self.device, torch.int64).contiguous()
+            cnt = torch.full((1,), ids.numel(), dtype=torch.int32, device=self.device)
+            L.check(L.lib.hl_episode_means(L.ptr(self._episode_sums_buf), L.ptr(self.episode_length_buf), L.ptr(ids),
+                                           L.ptr(cnt), rows, self.num_envs, float(self.dt), 1, L.ptr(means), L.stream()))
             for k, key in enumerate(self.episode_sums.keys()):
                 self.extras["episode"]["rew_" + key] = means[k]
-            self._episode_sums_buf[:, env_ids] = 0.0
         self.extras["time_outs"] = self.time_out_buf
         self.episode_length_buf[env_ids] = 0
 
