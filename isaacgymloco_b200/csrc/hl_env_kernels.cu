@@ -1050,7 +1050,11 @@ struct FusedArgs {
 #undef FK_GENERIC
 #undef FK_COMPACT
 #define FK_NS fk52
+#ifdef HL_EXP_TILE
+#define FK_EPB HL_EXP_TILE
+#else
 #define FK_EPB 52
+#endif
 #define FK_SCALAR_WARPS 2
 #ifdef HL_EXP_T288
 #define FK_THREADS 288
