@@ -232,6 +232,13 @@ int hl_select_and_terminal(const HlCfg* cfg, const HlEnvBuffers* bufs, const flo
 int hl_post_reset_fixup(const HlCfg* cfg, const HlEnvBuffers* bufs, const int64_t* env_ids,
                         const int32_t* n_ids_dev, int32_t with_reset_zero, int64_t n_envs, void* stream);
 
+/* ReplayBuffer.insert(states, next_states) -- rsl_rl/rsl_rl/storage/replay_buffer.py:52-68: row r of
+ * both (n_rows, width) inputs is written to ring row (step + r) mod buffer_rows; when more than
+ * buffer_rows rows arrive only the last buffer_rows survive (the reference's second slice
+ * overwrites the first).  One launch for both tensors. */
+int hl_ring_insert(const float* states, const float* next_states, float* ring_states, float* ring_next,
+                   int64_t n_rows, int32_t width, int64_t buffer_rows, int64_t step, void* stream);
+
 /* reset_idx's episode logging -- LR:346-350: for every reward row k,
  *   means_out[k] = mean_{e in env_ids}( episode_sums[k][e] / clip(episode_length_buf[e], min=1) / dt )
  * (one launch instead of 21 masked-mean chains; the id count stays on the device).  With

@@ -303,3 +303,34 @@ extern "C" int hl_minibatch_gather(const HlGatherFields* f, const int64_t* indic
   HL_CHECK_LAUNCH();
   return HL_OK;
 }
+
+
+// ============================================================================= replay ring insert
+__global__ void __launch_bounds__(256) hl_ring_insert_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                             float* __restrict__ ra, float* __restrict__ rb, long long n_rows,
+                                                             int width, long long size, long long step) {
+  hl_pdl_enter();
+  const long long total = n_rows * width;
+  const long long first = n_rows > size ? n_rows - size : 0;   // earlier rows would be overwritten
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / width;
+    if (r < first) continue;
+    const long long d = ((step + r) % size) * width + (i - r * width);
+    ra[d] = a[i];
+    rb[d] = b[i];
+  }
+}
+
+extern "C" int hl_ring_insert(const float* states, const float* next_states, float* ring_states, float* ring_next,
+                              int64_t n_rows, int32_t width, int64_t buffer_rows, int64_t step, void* stream) {
+  HL_CHECK_ARG(states && next_states && ring_states && ring_next, "null pointer");
+  HL_CHECK_ARG(width > 0 && buffer_rows > 0 && step >= 0 && step < buffer_rows, "bad ring geometry");
+  if (n_rows <= 0) return HL_OK;
+  const long long total = (long long)n_rows * width;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  hl_launch(hl_ring_insert_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, states, next_states, ring_states,
+            ring_next, (long long)n_rows, (int)width, (long long)buffer_rows, (long long)step);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}

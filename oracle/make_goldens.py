@@ -251,6 +251,32 @@ def mint_minibatch():
     print(f"[golden] minibatch: {len(batches)} batches")
 
 
+REPLAY_INSERTS = (5, 9, 4, 12, 1, 17, 3)   # rows per insert into a 16-row ring: plain, wrapping, > buffer_size
+
+
+def replay_inputs(obs_dim=30, seed=88):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(k, obs_dim, generator=g), torch.randn(k, obs_dim, generator=g)) for k in REPLAY_INSERTS]
+
+
+def mint_replay():
+    """The reference's ReplayBuffer (replay_buffer.py) on CPU: a sequence of inserts with wrap-around,
+    then sampled minibatches under a fixed numpy seed."""
+    H.install_stubs()
+    from rsl_rl.storage.replay_buffer import ReplayBuffer
+    rb = ReplayBuffer(30, 16, "cpu")
+    out = {}
+    for i, (a, b) in enumerate(replay_inputs()):
+        rb.insert(a, b)
+        out[f"states_{i}"], out[f"next_{i}"] = rb.states.numpy().copy(), rb.next_states.numpy().copy()
+        out[f"meta_{i}"] = np.array([rb.step, rb.num_samples], dtype=np.int64)
+    np.random.seed(123)
+    for j, (s_, n_) in enumerate(rb.feed_forward_generator(3, 7)):
+        out[f"mb_s{j}"], out[f"mb_n{j}"] = s_.numpy().copy(), n_.numpy().copy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "replay.npz"), **out)
+    print("[golden] replay")
+
+
 def mint_amp():
     H.install_stubs()
     np.random.seed(31)
@@ -327,6 +353,7 @@ def main():
     mint_gae()
     mint_record()
     mint_minibatch()
+    mint_replay()
     mint_amp()
 
 

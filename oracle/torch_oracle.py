@@ -623,6 +623,37 @@ def mini_batches(storage, num_mini_batches, num_epochs, indices):
             yield tuple(flat[k][idx] for k in MINIBATCH_ORDER)
 
 
+# --------------------------------------------------------------------------- f3: AMP replay ring
+class OracleReplayBuffer:
+    """rsl_rl/rsl_rl/storage/replay_buffer.py:35-74 restated (ring insert with the two-slice wrap,
+    host-RNG sampling)."""
+
+    def __init__(self, obs_dim, buffer_size, device="cpu"):
+        self.states = torch.zeros(buffer_size, obs_dim, device=device)
+        self.next_states = torch.zeros(buffer_size, obs_dim, device=device)
+        self.buffer_size, self.device, self.step, self.num_samples = buffer_size, device, 0, 0
+
+    def insert(self, states, next_states):
+        num, size = states.shape[0], self.buffer_size
+        end = self.step + num
+        if end > size:
+            head = size - self.step
+            self.states[self.step:size] = states[:head]
+            self.next_states[self.step:size] = next_states[:head]
+            self.states[:end - size] = states[head:]
+            self.next_states[:end - size] = next_states[head:]
+        else:
+            self.states[self.step:end] = states
+            self.next_states[self.step:end] = next_states
+        self.num_samples = min(size, max(end, self.num_samples))
+        self.step = (self.step + num) % size
+
+    def feed_forward_generator(self, num_mini_batch, mini_batch_size):
+        for _ in range(num_mini_batch):
+            idx = np.random.choice(self.num_samples, size=mini_batch_size)
+            yield self.states[idx], self.next_states[idx]
+
+
 # --------------------------------------------------------------------------- a16-a19: AMP
 _EPS = np.finfo(float).eps * 4.0        # rsl_rl/rsl_rl/utils/utils.py:35
 

@@ -249,6 +249,39 @@ def test_mini_batch_gather_full_size_properties():
     assert st.gather_batch(idx[:0])[0].shape == (0, 270)
 
 
+def test_replay_buffer_vs_reference_golden():
+    """ReplayBuffer (hl_ring_insert + hl_minibatch_gather) vs the reference's ReplayBuffer: inserts
+    that wrap and that exceed the ring, step / num_samples bookkeeping, sampled minibatches."""
+    from isaacgymloco_b200.replay_buffer import ReplayBuffer
+    from test_oracle_golden import replay_inputs
+    gold = load_golden("replay.npz")
+    rb = ReplayBuffer(30, 16, "cuda:0")
+    for i, (a, b) in enumerate(replay_inputs()):
+        rb.insert(a.cuda(), b.cuda())
+        np.testing.assert_array_equal(rb.states.cpu().numpy(), gold[f"states_{i}"])
+        np.testing.assert_array_equal(rb.next_states.cpu().numpy(), gold[f"next_{i}"])
+        assert [rb.step, rb.num_samples] == list(gold[f"meta_{i}"])
+    np.random.seed(123)
+    for j, (s_, n_) in enumerate(rb.feed_forward_generator(3, 7)):
+        np.testing.assert_array_equal(s_.cpu().numpy(), gold[f"mb_s{j}"])
+        np.testing.assert_array_equal(n_.cpu().numpy(), gold[f"mb_n{j}"])
+    with pytest.raises(RuntimeError):
+        rb.insert(torch.zeros(40, 30, device="cuda"), torch.zeros(40, 30, device="cuda"))
+    # config-4 sizes against the oracle on the same device
+    from oracle import torch_oracle as O
+    big, ob = ReplayBuffer(30, 100000, "cuda:0"), O.OracleReplayBuffer(30, 100000, "cuda")
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for _ in range(8):
+        a, b = torch.randn(16384, 30, device="cuda", generator=g), torch.randn(16384, 30, device="cuda", generator=g)
+        big.insert(a, b); ob.insert(a, b)
+    assert torch.equal(big.states, ob.states) and torch.equal(big.next_states, ob.next_states)
+    assert (big.step, big.num_samples) == (ob.step, ob.num_samples)
+    np.random.seed(9); x = list(big.feed_forward_generator(2, 4096))
+    np.random.seed(9); y = list(ob.feed_forward_generator(2, 4096))
+    for (s1, n1), (s2, n2) in zip(x, y):
+        assert torch.equal(s1, s2) and torch.equal(n1, n2)
+
+
 def test_amp_frame_blend_vs_reference_golden():
     gold = load_golden("amp.npz")
     ld = _loader(gold)

@@ -93,6 +93,28 @@ def test_mini_batch_generator():
             np.testing.assert_array_equal(x.numpy(), gold[f"b{bi}_f{fi}"], err_msg=f"batch {bi} field {fi}")
 
 
+REPLAY_INSERTS = (5, 9, 4, 12, 1, 17, 3)   # mirrors oracle/make_goldens.py
+
+
+def replay_inputs(obs_dim=30, seed=88):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(k, obs_dim, generator=g), torch.randn(k, obs_dim, generator=g)) for k in REPLAY_INSERTS]
+
+
+def test_replay_buffer():
+    gold = load_golden("replay.npz")
+    rb = O.OracleReplayBuffer(30, 16)
+    for i, (a, b) in enumerate(replay_inputs()):
+        rb.insert(a, b)
+        np.testing.assert_array_equal(rb.states.numpy(), gold[f"states_{i}"])
+        np.testing.assert_array_equal(rb.next_states.numpy(), gold[f"next_{i}"])
+        assert [rb.step, rb.num_samples] == list(gold[f"meta_{i}"])
+    np.random.seed(123)
+    for j, (s_, n_) in enumerate(rb.feed_forward_generator(3, 7)):
+        np.testing.assert_array_equal(s_.numpy(), gold[f"mb_s{j}"])
+        np.testing.assert_array_equal(n_.numpy(), gold[f"mb_n{j}"])
+
+
 def _table(gold):
     clips = [torch.from_numpy(gold[f"clip{i}"]) for i in range(len(gold["frame_durations"]))]
     return O.OracleMotionTable(clips, gold["frame_durations"], gold["weights_raw"], 0.02)
