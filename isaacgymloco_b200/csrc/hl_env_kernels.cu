@@ -45,7 +45,7 @@ static int check_cfg(const HlCfg* c, const HlEnvBuffers* b) {
 }
 
 // ============================================================================= a1: PD torques
-// LR:658-688.  One thread per env: 3+6+3 independent 128-bit loads in flight, 3 128-bit stores.
+// LR:658-688.  Three threads per env (one float4 of every 12-wide row each).
 struct PdCfg {
   float action_scale, hip_reduction, sim_dt;
   int control_type;
@@ -62,38 +62,38 @@ __device__ __forceinline__ float pd_one(const PdCfg& c, int d, float action, flo
   else tq = scaled;
   return hl_clampf(tq, -c.torque_limits[d], c.torque_limits[d]);
 }
-__global__ void __launch_bounds__(128) hl_pd_torque_vec_kernel(PdCfg c, const float* __restrict__ actions, long long a_stride,
+__global__ void __launch_bounds__(192) hl_pd_torque_vec_kernel(PdCfg c, const float* __restrict__ actions, long long a_stride,
                                                                const float4* __restrict__ dof_state,
                                                                const float4* __restrict__ motor_strength,
                                                                const float* __restrict__ kp, const float* __restrict__ kd,
                                                                const float4* __restrict__ last_dof_vel, float4* __restrict__ out,
                                                                float4* __restrict__ target_out, long long n) {
+  // three threads per env, one leg-and-a-third (4 dofs = one float4 of every 12-wide row) each:
+  // 5 independent 128-bit loads in flight per thread, 196,608 threads for 65,536 envs
   hl_pdl_enter();
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  const float4* a4 = reinterpret_cast<const float4*>(actions + e * a_stride);
-  float4 a[3], m[3], dv[6], lv[3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) a[j] = __ldg(a4 + j);
-#pragma unroll
-  for (int j = 0; j < 3; ++j) m[j] = __ldg(motor_strength + e * 3 + j);
-#pragma unroll
-  for (int j = 0; j < 6; ++j) dv[j] = __ldg(dof_state + e * 6 + j);
-#pragma unroll
-  for (int j = 0; j < 3; ++j) lv[j] = c.control_type == 1 ? __ldg(last_dof_vel + e * 3 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * 3) return;
+  const long long e = t / 3;
+  const int j = (int)(t - e * 3);
+  const float4 a = __ldg(reinterpret_cast<const float4*>(actions + e * a_stride) + j);
+  const float4 m = __ldg(motor_strength + t);
+  const float4 dv0 = __ldg(dof_state + 2 * t), dv1 = __ldg(dof_state + 2 * t + 1);
+  const float4 lv = c.control_type == 1 ? __ldg(last_dof_vel + t) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float kpe = __ldg(kp + e), kde = __ldg(kd + e);
-  const float* af = reinterpret_cast<const float*>(a);
-  const float* mf = reinterpret_cast<const float*>(m);
-  const float* df = reinterpret_cast<const float*>(dv);
-  const float* lf = reinterpret_cast<const float*>(lv);
-  float tq[12], tg[12];
+  const float af[4] = {a.x, a.y, a.z, a.w}, mf[4] = {m.x, m.y, m.z, m.w}, lf[4] = {lv.x, lv.y, lv.z, lv.w};
+  const float pos[4] = {dv0.x, dv0.z, dv1.x, dv1.z}, vel[4] = {dv0.y, dv0.w, dv1.y, dv1.w};
+  float tq[4], tg[4];
 #pragma unroll
-  for (int d = 0; d < 12; ++d) tq[d] = pd_one(c, d, af[d], mf[d], df[2 * d], df[2 * d + 1], kpe, kde, lf[d], &tg[d]);
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    out[e * 3 + j] = make_float4(tq[4 * j], tq[4 * j + 1], tq[4 * j + 2], tq[4 * j + 3]);
-    if (target_out) target_out[e * 3 + j] = make_float4(tg[4 * j], tg[4 * j + 1], tg[4 * j + 2], tg[4 * j + 3]);
+  for (int i = 0; i < 4; ++i) {
+    // dof d = 4j + i; its constants picked with selects on j (uniform constant-bank operands)
+    float r;
+    if (j == 0) r = pd_one(c, i, af[i], mf[i], pos[i], vel[i], kpe, kde, lf[i], &tg[i]);
+    else if (j == 1) r = pd_one(c, 4 + i, af[i], mf[i], pos[i], vel[i], kpe, kde, lf[i], &tg[i]);
+    else r = pd_one(c, 8 + i, af[i], mf[i], pos[i], vel[i], kpe, kde, lf[i], &tg[i]);
+    tq[i] = r;
   }
+  out[t] = make_float4(tq[0], tq[1], tq[2], tq[3]);
+  if (target_out) target_out[t] = make_float4(tg[0], tg[1], tg[2], tg[3]);
 }
 // fallback for unaligned / oddly strided action views: one thread per (env, dof)
 __global__ void __launch_bounds__(256) hl_pd_torque_kernel(PdCfg c, const float* __restrict__ actions, long long a_stride,
@@ -137,7 +137,7 @@ extern "C" int hl_pd_torque(const HlCfg* cfg, const float* actions, int64_t a_st
   const bool vec = al16(actions) && (a_stride % 4 == 0) && al16(dof_state) && al16(motor_strength) && al16(torques_out) &&
                    (!target_out || al16(target_out)) && (!last_dof_vel || al16(last_dof_vel));
   if (vec) {
-    hl_launch(hl_pd_torque_vec_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, (cudaStream_t)stream,
+    hl_launch(hl_pd_torque_vec_kernel, dim3((unsigned)((n * 3 + 191) / 192)), dim3(192), 0, (cudaStream_t)stream,
         pc, actions, a_stride, (const float4*)dof_state, (const float4*)motor_strength, kp, kd, (const float4*)last_dof_vel,
         (float4*)torques_out, (float4*)target_out, n);
   } else {
