@@ -35,8 +35,11 @@ __global__ void __launch_bounds__(BLEND_SAMPLES) hl_amp_blend_kernel(
     const int lo = (int)flo, hi = (int)fhi;
     const float blend = (float)(pn - flo);
     BlendRow r;
-    r.lo = clip_offset[ti] + lo;
-    r.hi = clip_offset[ti] + hi;
+    // times outside [0, len (n-1)/n] index past the clip (the reference raises IndexError, the host
+    // wrapper does too); the reads are clamped to the clip so the kernel itself stays memory-safe
+    const int last = (int)clip_nf[ti] - 1;
+    r.lo = clip_offset[ti] + min(max(lo, 0), last);
+    r.hi = clip_offset[ti] + min(max(hi, 0), last);
     r.blend = blend;
     if (lo_out) lo_out[smp] = lo;
     if (hi_out) hi_out[smp] = hi;

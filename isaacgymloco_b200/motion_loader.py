@@ -180,8 +180,17 @@ class AMPLoader:
     # ------------------------------------------------------------------ kernels
     def get_full_frame_at_time_batch(self, traj_idxs, times, return_indices=False):
         """ML:231-255 -> (B,49) fp32 on the device.  traj_idxs: int array, times: float64 array."""
-        idx_t = torch.as_tensor(np.asarray(traj_idxs, dtype=np.int64)).to(self.device, non_blocking=True)
-        times_t = torch.as_tensor(np.asarray(times, dtype=np.float64)).to(self.device, non_blocking=True)
+        ti = np.asarray(traj_idxs, dtype=np.int64)
+        tm = np.asarray(times, dtype=np.float64)
+        if ti.size:
+            # same failure as the reference's frame lookup (ML:243-244): an index past the clip
+            if ti.min() < 0 or ti.max() >= len(self.trajectories_full):
+                raise IndexError("trajectory index out of range")
+            pn = tm / self.trajectory_lens[ti] * self.trajectory_num_frames[ti]
+            if np.floor(pn).min() < -self.trajectory_num_frames[ti].min() or (np.ceil(pn) > self.trajectory_num_frames[ti] - 1).any():
+                raise IndexError("frame index out of bounds for the clip (time beyond its last frame)")
+        idx_t = torch.as_tensor(ti).to(self.device, non_blocking=True)
+        times_t = torch.as_tensor(tm).to(self.device, non_blocking=True)
         return self.get_full_frame_at_time_batch_device(idx_t, times_t, return_indices)
 
     def get_full_frame_at_time_batch_device(self, idx_t, times_t, return_indices=False):

@@ -375,3 +375,56 @@ def test_env_writes_rollout_slots_in_place():
     assert envs[1].obs_buf.data_ptr() == stores[1].obs_slot(1).data_ptr()
     envs[1].bind_rollout(None)
     assert envs[1].obs_buf.data_ptr() != stores[1].obs_slot(1).data_ptr()
+
+
+@pytest.mark.parametrize("oracle_dev", ["cpu", "cuda"])
+def test_adversarial_thresholds(oracle_dev):
+    """Inputs placed exactly on every comparison threshold of the path (SURVEY.md §8c Tier 2):
+    contact-force norms at 1.0 / 0.1 / max_contact_force and one ulp above, foot Fz at 1.0,
+    episode_length at 999/1000/1001, v_z at -5, base exactly on the terrain border, zero commands.
+    Flags and ids must be bit-exact, floats within tolerance."""
+    from gpu_helpers import assert_close, assert_equal, compare_snapshots, make_env
+    from isaacgymloco_b200 import config as C, synthetic as S
+    n = 1024
+    cfg = C.aliengo("stairs", num_envs=n,
+                    index_math=C.INDEX_MATH_TORCH_CPU if oracle_dev == "cpu" else C.INDEX_MATH_TORCH_CUDA)
+    hf = S.make_terrain(cfg, seed=5)
+    state = S.make_state(cfg, n, hf, seed=310)
+    nb = cfg.num_bodies
+    cf = state["contact_forces"].view(n, nb, 3)
+    up = lambda x: float(np.nextafter(np.float32(x), np.float32(np.inf)))
+    dn = lambda x: float(np.nextafter(np.float32(x), np.float32(-np.inf)))
+    base = cfg.termination_contact_indices[0]
+    pen = [b for b in cfg.penalised_contact_indices if b != base][0]
+    foot = cfg.feet_indices[0]
+    cf[0:64, base] = 0.0
+    cf[0:16, base, 2] = 1.0                 # ||F|| == 1.0: no termination
+    cf[16:32, base, 2] = up(1.0)            # one ulp above: termination
+    cf[32:48, base, 0], cf[32:48, base, 1] = 0.6, 0.8      # 0.36 + 0.64 = 1.0 in exact arithmetic; fp32 decides
+    cf[64:80, pen] = 0.0
+    cf[64:72, pen, 1] = 0.1                 # collision threshold
+    cf[72:80, pen, 1] = up(0.1)
+    cf[96:112, foot] = 0.0
+    cf[96:104, foot, 2] = 1.0               # contact flag threshold (> 1.0)
+    cf[104:112, foot, 2] = up(1.0)
+    cf[112:120, foot, 2] = float(cfg.max_contact_force)
+    cf[120:128, foot, 2] = up(cfg.max_contact_force)
+    state["episode_length_buf"][128:160] = torch.tensor([998, 999, 1000, 1001] * 8)
+    state["root_states"][160:168, 9] = -5.0
+    state["root_states"][168:176, 9] = dn(-5.0)
+    state["root_states"][176:184, 0] = 0.0                  # on the lower terrain border
+    state["root_states"][184:192, 1] = 0.0
+    state["commands"][192:224] = 0.0
+    state["root_states"][224:232, 3:7] = torch.tensor([0.0, 0.0, 1.0, 0.0])   # yaw = pi: heading wrap
+    state["root_states"][232:240, 3:7] = torch.tensor([0.0, 0.0, -1.0, 0.0])
+    noise = S.make_noise(n, seed=311)
+    targets = S.make_reset_targets(cfg, state, hf, seed=312)
+    oenv, oids, oterm, oamp = _oracle_step(cfg, state, hf, noise, targets, oracle_dev)
+    env = make_env(cfg, state, hf, targets, noise)
+    ids, term_obs, term_amp = env.post_physics_step()
+    assert_equal(ids, oids, "env_ids")
+    want = set(range(16, 32)) | {130 + 4 * k for k in range(8)} | {131 + 4 * k for k in range(8)} | set(range(168, 176))
+    assert want <= set(ids.cpu().tolist()), "threshold envs that must reset"
+    assert_close(term_obs, oterm, "termination_privileged_obs")
+    assert_close(term_amp, oamp, "terminal_amp_states")
+    compare_snapshots(env.snapshot(), oenv.snapshot())

@@ -403,3 +403,34 @@ def test_amp_terminal_patch_config4():
     np.testing.assert_array_equal(x.cpu().numpy(), want.numpy())
     x0 = disc.assemble_input(s.cuda(), sn.cuda(), None)
     np.testing.assert_array_equal(x0.cpu().numpy(), torch.cat([s, sn], -1).numpy())
+
+
+def test_amp_blend_adversarial_times():
+    """Times exactly on frame boundaries (blend 0), at t=0 and at the clip end (lo == hi == last
+    frame), plus antipodal / identical quaternion pairs through the slerp (its 1/angle quirk included)."""
+    from oracle import torch_oracle as O
+    gold = load_golden("amp.npz")
+    ld = _loader(gold)
+    tab = O.OracleMotionTable([torch.from_numpy(gold[f"clip{i}"]) for i in range(7)], gold["frame_durations"],
+                              gold["weights_raw"], 0.02)
+    idx, times = [], []
+    for c in range(7):
+        length, nf = tab.trajectory_lens[c], int(tab.trajectory_num_frames[c])
+        for k in (0, 1, nf // 2, nf - 2, nf - 1):
+            idx.append(c); times.append(length * k / nf)                 # p*n lands on (or an ulp off) an integer
+        idx += [c, c]
+        times += [0.0, np.nextafter(length * (nf - 1) / nf, 0.0)]
+    idx, times = np.array(idx), np.array(times, dtype=np.float64)
+    # k = nf-1 can land one ulp above the last frame (then the reference itself raises): keep the valid ones
+    ok = np.ceil(times / tab.trajectory_lens[idx] * tab.trajectory_num_frames[idx]) <= tab.trajectory_num_frames[idx] - 1
+    assert ok.sum() >= len(ok) - 7
+    idx, times = idx[ok], times[ok]
+    with pytest.raises(IndexError):    # the reference indexes past the clip for t = len (ML:243-244)
+        ld.get_full_frame_at_time_batch(np.array([0]), np.array([tab.trajectory_lens[0]]))
+    want, lo, hi = tab.get_full_frame_at_time_batch(idx, times)
+    got, glo, ghi = ld.get_full_frame_at_time_batch(idx, times, return_indices=True)
+    np.testing.assert_array_equal(glo.cpu().numpy(), lo.astype(np.int32))
+    np.testing.assert_array_equal(ghi.cpu().numpy(), hi.astype(np.int32))
+    lerp_cols = [c for c in range(49) if not 3 <= c < 7]
+    np.testing.assert_array_equal(got.cpu().numpy()[:, lerp_cols], want.numpy()[:, lerp_cols])
+    np.testing.assert_allclose(got.cpu().numpy()[:, 3:7], want.numpy()[:, 3:7], rtol=1e-5, atol=1e-6, equal_nan=True)
