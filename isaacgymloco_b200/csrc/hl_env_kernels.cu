@@ -226,25 +226,35 @@ __device__ __forceinline__ float hl_warp_scan_env(const HlCfg& c, const HlEnvBuf
       const ScanAxis axi = hl_scan_axis_x(qz, qw, c.px[lane < c.n_px ? lane : 0]);
       const ScanAxis axj = hl_scan_axis_y(qz, qw, c.py[lane < c.n_py ? lane : 0]);
       HeightNoise hn;
-      for (int it = 0; it * 32 < P; ++it) {
+      // pass 1: every gather of the env in flight (P <= 256 -> at most 8 per lane); pass 2: outputs
+      int hraw[8], pxs[8], pys[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        hraw[it] = 0; pxs[it] = 0; pys[it] = 0;
+        if (it * 32 < P) {   // warp-uniform
+          const int p = it * 32 + lane;
+          const int pc = p < P ? p : P - 1;
+          const int i = pc / c.n_py, j = pc - i * c.n_py;
+          ScanAxis ai, aj;
+          ai.a = __shfl_sync(0xffffffffu, axi.a, i);
+          ai.c = __shfl_sync(0xffffffffu, axi.c, i);
+          aj.a = __shfl_sync(0xffffffffu, axj.a, j);
+          aj.c = __shfl_sync(0xffffffffu, axj.c, j);
+          hraw[it] = hl_scan_point(c, b, posx, posy, c.px[i], c.py[j], ai, aj, &pxs[it], &pys[it]);
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        if (it * 32 >= P) break;
         const int p = it * 32 + lane;
-        const int pc = p < P ? p : P - 1;
-        const int i = pc / c.n_py, j = pc - i * c.n_py;
-        ScanAxis ai, aj;
-        ai.a = __shfl_sync(0xffffffffu, axi.a, i);
-        ai.c = __shfl_sync(0xffffffffu, axi.c, i);
-        aj.a = __shfl_sync(0xffffffffu, axj.a, j);
-        aj.c = __shfl_sync(0xffffffffu, axj.c, j);
-        int px, py;
-        const int hraw = hl_scan_point(c, b, posx, posy, c.px[i], c.py[j], ai, aj, &px, &py);
-        const float mh = (float)hraw * c.vertical_scale;
+        const float mh = (float)hraw[it] * c.vertical_scale;
         if (o.priv_heights && !o.u187 && (it & 3) == 0) hn.refill(b, genv, it >> 2, lane, noise_stream);
         float u = 0.5f;
         if (o.priv_heights && c.add_noise) u = o.u187 ? (p < P ? o.u187[p] : 0.5f) : hn.get(it, lane);
         if (p < P) {
           if (o.measured) o.measured[p] = mh;
           if (o.keep) o.keep[it] = mh;
-          if (o.idx) { o.idx[2 * p] = px; o.idx[2 * p + 1] = py; }
+          if (o.idx) { o.idx[2 * p] = pxs[it]; o.idx[2 * p + 1] = pys[it]; }
           if (o.priv_heights) {
             float hv = hl_obs_height(c, posz, mh, u);
             if (o.clip) hv = hl_clampf(hv, -c.clip_obs, c.clip_obs);
