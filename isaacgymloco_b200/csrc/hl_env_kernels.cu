@@ -951,9 +951,9 @@ __global__ void __launch_bounds__(1024) hl_select_ids_kernel(const uint8_t* __re
       const int t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += t;
     }
+    const int running = running_s;   // read before the barrier: warp 0 overwrites it right after
     if (lane == 31) warp_tot[wid] = incl;
     __syncthreads();
-    const int running = running_s;
     if (wid == 0) {
       int wt = warp_tot[lane], wi = wt;
 #pragma unroll
