@@ -445,7 +445,9 @@ def aliengo(task: str = "flat", num_envs: int = 4096, **overrides) -> HotPathCfg
     elif task == "amp":
         sc = dict(_FLAT_SCALES)
         sc["base_height"] = -10.0                      # aliengo_amp_config.py:226
-        cfg = HotPathCfg(num_envs=num_envs, reward_scales=sc)
+        # aliengo_amp_config.py has no `termination` class: check_termination (LR:266-283) then keeps
+        # only the contact and time-out clauses
+        cfg = HotPathCfg(num_envs=num_envs, reward_scales=sc, out_of_border=False, fall_down=False)
     elif task == "stairs":
         cfg = HotPathCfg(
             num_envs=num_envs, reward_scales=dict(_STAIRS_SCALES), terrain_length=10.0,
@@ -472,11 +474,23 @@ def _scales_to_dict(obj) -> Dict[str, float]:
             and isinstance(getattr(obj, k), (int, float))}
 
 
-def from_reference_cfg(rc, num_envs: Optional[int] = None, sim_dt: float = 0.005) -> HotPathCfg:
+def from_reference_cfg(rc, num_envs: Optional[int] = None, sim_dt: float = 0.005, env=None) -> HotPathCfg:
     """Build from an instance of the reference's nested config classes (duck-typed; this module
-    never imports the reference)."""
+    never imports the reference).  `env` (optional) = the reference LeggedRobot being patched: its
+    own body index tensors (`feet_indices`, `penalised_contact_indices`,
+    `termination_contact_indices`, resolved from the asset at LR:1207-1218) then replace the
+    aliengo defaults."""
     t, ctl, rw, nz, norm = rc.terrain, rc.control, rc.rewards, rc.noise, rc.normalization
     term = getattr(rc, "termination", None)
+    idx = {}
+    for name in ("feet_indices", "penalised_contact_indices", "termination_contact_indices"):
+        v = getattr(env, name, None) if env is not None else None
+        if v is not None:
+            idx[name] = [int(x) for x in (v.tolist() if hasattr(v, "tolist") else v)]
+    asset = getattr(rc, "asset", None)
+    if "termination_contact_indices" not in idx and asset is not None and \
+            list(getattr(asset, "terminate_after_contacts_on", ["base"])) == []:
+        idx["termination_contact_indices"] = []          # e.g. aliengo_recover_config.py:97
     cfg = HotPathCfg(
         num_envs=num_envs or rc.env.num_envs,
         control_type=ctl.control_type, stiffness=list(ctl.stiffness.values())[0],
@@ -508,5 +522,6 @@ def from_reference_cfg(rc, num_envs: Optional[int] = None, sim_dt: float = 0.005
         noise_height=nz.noise_scales.height_measurements,
         disturbance_interval=getattr(rc.domain_rand, "disturbance_interval", 8),
         push_interval_s=getattr(rc.domain_rand, "push_interval_s", 16),
+        **idx,
     )
     return cfg

@@ -128,3 +128,26 @@ def test_mocap_binary_cache_round_trip(tmp_path):
         back = AMPLoader.read_cache(path)
         for i, fr in enumerate(back["frames"]):
             np.testing.assert_array_equal(fr[:, :49].astype(np.float32), gold[f"clip{i}"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/legged_gym"), reason="needs the reference's config classes (build container only)")
+@pytest.mark.parametrize("task", ["flat", "stairs", "amp", "recover"])
+def test_presets_equal_the_reference_config_classes(task):
+    """config.aliengo(task) (the constants that travel to the GPU box) == from_reference_cfg() of the
+    reference's own AlienGo*Cfg class: every field of the C struct, the reward table and the noise vector."""
+    import ctypes
+    from oracle import ref_harness as H
+    from isaacgymloco_b200 import config as C
+    rc = H.reference_cfg(task)
+    a = C.from_reference_cfg(rc, num_envs=4096, sim_dt=0.005)
+    b = C.aliengo(task, num_envs=4096)
+    ca, cb = a.to_c(), b.to_c()
+    for name, _ in C.HlCfg._fields_:
+        va, vb = getattr(ca, name), getattr(cb, name)
+        if isinstance(va, ctypes.Array):
+            va, vb = list(va), list(vb)
+        assert va == vb, name
+    (na, sa), (nb, sb) = a.active_terms(), b.active_terms()
+    assert list(na) == list(nb) and np.array_equal(np.asarray(sa), np.asarray(sb))
+    assert list(a.episode_sum_names()) == list(b.episode_sum_names())
+    assert np.array_equal(np.asarray(a.noise_scale_vec()), np.asarray(b.noise_scale_vec()))
