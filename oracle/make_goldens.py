@@ -29,6 +29,7 @@ ENV_CASES = [
     dict(name="allterms", task="stairs", n=128, seed=14, all_terms=True),
     dict(name="plane", task="flat", n=64, seed=15, plane=True),
     dict(name="flat_noreset", task="flat", n=64, seed=16, no_reset=True),
+    dict(name="amp", task="amp", n=96, seed=33),     # no `termination` cfg class: contact + time-out clauses only
 ]
 
 
