@@ -151,3 +151,28 @@ def test_presets_equal_the_reference_config_classes(task):
     assert list(na) == list(nb) and np.array_equal(np.asarray(sa), np.asarray(sb))
     assert list(a.episode_sum_names()) == list(b.episode_sum_names())
     assert np.array_equal(np.asarray(a.noise_scale_vec()), np.asarray(b.noise_scale_vec()))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/legged_gym"), reason="needs the reference's URDF (build container only)")
+def test_aliengo_dof_constants_equal_the_urdf():
+    """The joint limits / efforts / velocities the reference reads through Isaac Gym's asset loader
+    (LR:565-580) come from aliengo.urdf; the constants in config.py must be those numbers, in the
+    reference's DOF order (FL, FR, RL, RR x hip, thigh, calf: LR:1145)."""
+    import xml.etree.ElementTree as ET
+    from oracle import ref_harness as H
+    from isaacgymloco_b200 import config as C
+    root = ET.parse("/root/reference/legged_gym/resources/robots/aliengo/urdf/aliengo.urdf").getroot()
+    lim = {j.get("name"): j.find("limit").attrib for j in root.findall("joint") if j.get("type") == "revolute"}
+    rc = H.reference_cfg("flat")
+    cfg = C.aliengo("flat")
+    cfg.soft_dof_pos_limit = 1.0        # raw limits
+    t = cfg.dof_tables()
+    k = 0
+    for leg in ("FL", "FR", "RL", "RR"):
+        for joint in ("hip", "thigh", "calf"):
+            a = lim[f"{leg}_{joint}_joint"]
+            assert np.float32(a["effort"]) == t["torque_limits"][k]
+            assert np.float32(a["velocity"]) == t["dof_vel_limits"][k]
+            np.testing.assert_allclose([t["dof_pos_lo"][k], t["dof_pos_hi"][k]], [float(a["lower"]), float(a["upper"])], rtol=1e-6)
+            assert np.float32(rc.init_state.default_joint_angles[f"{leg}_{joint}_joint"]) == t["default_dof_pos"][k]
+            k += 1
