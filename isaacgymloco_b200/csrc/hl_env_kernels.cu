@@ -196,9 +196,11 @@ struct ScanOut {
   float* keep;         // optional: lane-private copy of this lane's heights, keep[it]
 };
 
+// it_mod / it_rem: this warp only handles the 32-point iterations with it % it_mod == it_rem (the
+// post-reset fix-up spreads one env over several warps); 1 / 0 = all of them.
 __device__ __forceinline__ float hl_warp_scan_env(const HlCfg& c, const HlEnvBuffers& b, const float* root,
                                                   unsigned long long genv, int lane, bool do_heights, bool want_base,
-                                                  const ScanOut& o, unsigned noise_stream) {
+                                                  const ScanOut& o, unsigned noise_stream, int it_mod = 1, int it_rem = 0) {
   float qz, qw;
   hl_yaw_quat(root + 3, qz, qw);
   const float posx = root[0], posy = root[1], posz = root[2];
@@ -231,7 +233,7 @@ __device__ __forceinline__ float hl_warp_scan_env(const HlCfg& c, const HlEnvBuf
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         hraw[it] = 0; pxs[it] = 0; pys[it] = 0;
-        if (it * 32 < P) {   // warp-uniform
+        if (it * 32 < P && (it % it_mod) == it_rem) {   // warp-uniform
           const int p = it * 32 + lane;
           const int pc = p < P ? p : P - 1;
           const int i = pc / c.n_py, j = pc - i * c.n_py;
@@ -243,12 +245,14 @@ __device__ __forceinline__ float hl_warp_scan_env(const HlCfg& c, const HlEnvBuf
           hraw[it] = hl_scan_point(c, b, posx, posy, c.px[i], c.py[j], ai, aj, &pxs[it], &pys[it]);
         }
       }
+      int pass = -1;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         if (it * 32 >= P) break;
+        if ((it % it_mod) != it_rem) continue;
         const int p = it * 32 + lane;
         const float mh = (float)hraw[it] * c.vertical_scale;
-        if (o.priv_heights && !o.u187 && (it & 3) == 0) hn.refill(b, genv, it >> 2, lane, noise_stream);
+        if (o.priv_heights && !o.u187 && (it >> 2) != pass) { pass = it >> 2; hn.refill(b, genv, pass, lane, noise_stream); }
         float u = 0.5f;
         if (o.priv_heights && c.add_noise) u = o.u187 ? (p < P ? o.u187[p] : 0.5f) : hn.get(it, lane);
         if (p < P) {
@@ -349,10 +353,14 @@ __device__ __forceinline__ void hl_stage_env(float* st, const HlCfg& c, const Hl
   v.ltq = st + WS_A + 72;
 }
 
-template <unsigned STAGES>  // 0 = take the mask at run time; otherwise everything else is compiled out
-__global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, unsigned stages_rt,
+template <unsigned STAGES, bool SPLIT = false>  // STAGES 0 = take the mask at run time; otherwise everything else is compiled out
+__global__ void __launch_bounds__(256, 3) hl_stage_kernel(HlCfg c, HlEnvBuffers b, unsigned stages_rt,
                                                        const long long* __restrict__ ids,
-                                                       const int* __restrict__ n_ids, long long n) {
+                                                       const int* __restrict__ n_ids, long long n, int parts) {
+  // parts > 1 (post-reset fix-up only): an env is spread over `parts` warps -- warp 0 ("lead") does the
+  // buffer resets, slot 0 / privileged_obs[0:51] and the roll, warps 1.. the height iterations
+  // it % (parts-1) == part-1 (scan + height part of privileged_obs): shorter dependent chains for the
+  // few hundred reset envs of a step.
   hl_pdl_enter();
   const unsigned stages = STAGES ? STAGES : stages_rt;
   const int lane = threadIdx.x & 31;
@@ -364,13 +372,19 @@ __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, 
   const int PD = hl_priv_dim(c);
   extern __shared__ __align__(16) float stage_smem[];
   float* st = stage_smem + (threadIdx.x >> 5) * hl_warp_stage_floats(B);
-  for (long long it0 = warp0; it0 < items; it0 += nwarps) {
+  const int np = (SPLIT && parts > 1) ? parts : 1;   // !SPLIT: folds to the one-warp-per-env code
+  for (long long w = warp0; w < items * np; w += nwarps) {
+    const long long it0 = w / np;
+    const int part = (int)(w - it0 * np);
+    const bool lead = part == 0;                      // np == 1: the only warp of the env
+    const bool scans = np == 1 || part > 0;           // does height iterations
+    const int it_mod = np == 1 ? 1 : np - 1, it_rem = np == 1 ? 0 : part - 1;
     const long long e = ids ? ids[it0] : it0;
     if (e < 0 || e >= n) continue;
     __syncwarp();   // the previous env's staged records are no longer read
     EnvView v;
     hl_stage_env(st, c, b, e, lane, (stages & HL_ST_RESET_ZERO) != 0, v);
-    if (stages & HL_ST_RESET_ZERO) {  // LR:323-329,350,361
+    if ((stages & HL_ST_RESET_ZERO) && lead) {  // LR:323-329,350,361
       if (lane < 12) {
         b.last_actions[e * 12 + lane] = 0.0f;
         b.last_last_actions[e * 12 + lane] = 0.0f;
@@ -409,6 +423,7 @@ __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, 
     s.time_out = b.time_out_buf[e] != 0;
     __syncwarp();
 
+    if (!lead) goto heights_only;   // (parts > 1) the other warps of the env: height iterations only
     if (stages & HL_ST_COUNTERS) {
       s.ep_len += 1;
       if (lane == 0) b.episode_length_buf[e] = s.ep_len;
@@ -443,8 +458,9 @@ __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, 
       s.cmd[2] = hl_heading_command(v.root + 3, s.cmd[3]);
       if (lane == 0) b.commands[e * 4 + 2] = s.cmd[2];
     }
+  heights_only:
     float myh[8];
-    const bool do_h = (stages & HL_ST_HEIGHTS) && c.measure_heights;
+    const bool do_h = (stages & HL_ST_HEIGHTS) && c.measure_heights && scans;
     const bool want_base = ((stages & HL_ST_REWARD) && hl_needs_base_height(c)) || (stages & HL_ST_BASE_HEIGHT);
     if (do_h || want_base) {
       ScanOut o;
@@ -454,17 +470,17 @@ __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, 
       o.u187 = nullptr;
       o.clip = false;
       o.keep = myh;
-      s.base_h = hl_warp_scan_env(c, b, v.root, (unsigned long long)s.gid, lane, do_h, want_base, o, 0u);
+      s.base_h = hl_warp_scan_env(c, b, v.root, (unsigned long long)s.gid, lane, do_h, want_base && lead, o, 0u, it_mod, it_rem);
       if ((stages & HL_ST_BASE_HEIGHT) && b.base_height_out && lane == 0) b.base_height_out[e] = s.base_h;
     }
-    if (stages & HL_ST_TERMINATION) {
+    if ((stages & HL_ST_TERMINATION) && lead) {
       hl_check_termination(c, v, s);
       if (lane == 0) {
         b.reset_buf[e] = s.reset;
         b.time_out_buf[e] = s.time_out;
       }
     }
-    if (stages & HL_ST_REWARD) {
+    if ((stages & HL_ST_REWARD) && lead) {
       const float rew = hl_compute_reward(c, b, v, s, b.episode_sums ? b.episode_sums + e : nullptr, n, lane == 0);
       if (lane == 0) b.rew_buf[e] = rew;
       if (lane < 4) {
@@ -477,7 +493,7 @@ __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, 
       const float cl = c.clip_obs;
       // history first (registers), then the new slot: safe when obs_buf_out aliases obs_buf_in
       float old[8];
-      if (!(stages & HL_ST_OBS_NOSHIFT)) {
+      if (!(stages & HL_ST_OBS_NOSHIFT) && lead) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int k = i * 32 + lane;
@@ -490,7 +506,7 @@ __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, 
           if (k < 225) b.obs_buf_out[e * 270 + 45 + k] = clip ? hl_clampf(old[i], -cl, cl) : old[i];
         }
       }
-      {
+      if (lead) {
         uint4 nb = make_uint4(0u, 0u, 0u, 0u);
         int cb, c0;
         hl_cur_noise_slot(P, cb, c0);
@@ -509,17 +525,19 @@ __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, 
           }
         }
       }
-      if (lane < 6) {
+      if (lane < 6 && lead) {
         float x = lane < 3 ? s.blv[lane] * c.obs_lin_vel : b.disturbance[e * B * 3 + (lane - 3)];
         if (clip) x = hl_clampf(x, -cl, cl);
         b.privileged_obs_buf[e * PD + 45 + lane] = x;
       }
-      if (c.measure_heights) {
+      if (c.measure_heights && scans) {
         HeightNoise hn;
         const float rz = v.root[2];
+        int pass = -1;
         for (int it = 0; it * 32 < P; ++it) {
+          if ((it % it_mod) != it_rem) continue;
           const int p = it * 32 + lane;
-          if (!b.noise_u187 && (it & 3) == 0) hn.refill(b, (unsigned long long)s.gid, it >> 2, lane, 0u);
+          if (!b.noise_u187 && (it >> 2) != pass) { pass = it >> 2; hn.refill(b, (unsigned long long)s.gid, pass, lane, 0u); }
           float u = 0.5f;
           if (c.add_noise) u = b.noise_u187 ? (p < P ? b.noise_u187[e * P + p] : 0.5f) : hn.get(it, lane);
           if (p < P) {
@@ -531,7 +549,7 @@ __global__ void __launch_bounds__(256) hl_stage_kernel(HlCfg c, HlEnvBuffers b, 
         }
       }
     }
-    if (stages & HL_ST_ROLL) {  // LR:235-241 (reads complete before writes: llact <- lact <- act)
+    if ((stages & HL_ST_ROLL) && lead) {  // LR:235-241 (reads complete before writes: llact <- lact <- act)
       __syncwarp();
       float la = 0.f, a = 0.f, dp = 0.f, dv = 0.f, tq = 0.f, rv = 0.f;
       if (lane < 12) {
@@ -565,14 +583,24 @@ static int launch_stage(const HlCfg* cfg, const HlEnvBuffers* bufs, unsigned sta
   if (ids) blocks = blocks < 148 * 8 ? blocks : 148 * 8;  // id lists are short; grid-stride covers the rest
   const size_t stage_smem = (size_t)8 * hl_warp_stage_floats(cfg->num_bodies) * sizeof(float);
   HL_CHECK_ARG(stage_smem <= 48 * 1024, "num_bodies too large for the per-warp staging area");
+  static const int fix_parts_env = [] { const char* e = getenv("HL_FIX_PARTS"); return e ? atoi(e) : 4; }();
+  // small shards are latency-bound (a few hundred reset envs on 148 SMs): spread each env over several
+  // warps; at 65,536 envs the extra staging costs more than the shorter chains save (measured)
+  const int fix_parts = (ids && cfg->measure_heights && cfg->mesh_type != 0 && fix_parts_env > 1 && n <= 16384) ? fix_parts_env : 1;
   constexpr unsigned FIX = HL_ST_HEIGHTS | HL_ST_OBS | HL_ST_OBS_NOSHIFT | HL_ST_OBS_CLIP | HL_ST_ROLL;
   const cudaStream_t st = (cudaStream_t)stream;
   if (stages == FIX)
-    hl_launch(hl_stage_kernel<FIX>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n);
+  {
+    if (fix_parts > 1) hl_launch(hl_stage_kernel<FIX, true>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, fix_parts);
+    else hl_launch(hl_stage_kernel<FIX, false>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, 1);
+  }
   else if (stages == (FIX | HL_ST_RESET_ZERO))
-    hl_launch(hl_stage_kernel<FIX | HL_ST_RESET_ZERO>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n);
+  {
+    if (fix_parts > 1) hl_launch(hl_stage_kernel<FIX | HL_ST_RESET_ZERO, true>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, fix_parts);
+    else hl_launch(hl_stage_kernel<FIX | HL_ST_RESET_ZERO, false>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, 1);
+  }
   else
-    hl_launch(hl_stage_kernel<0u>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n);
+    hl_launch(hl_stage_kernel<0u, false>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, 1);
   HL_CHECK_LAUNCH();
   return HL_OK;
 }
