@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HL_VERSION 100
+#define HL_VERSION 101
 
 #define HL_OK 0
 #define HL_E_INVALID 1   /* bad argument / inconsistent config */
@@ -166,7 +166,10 @@ typedef struct HlEnvBuffers {
   float* term_amp_out;            /* (N, 30) capacity or NULL */
   const float* term_noise_u45;    /* pre-drawn U[0,1) for the terminal rows, or NULL => Philox stream 1 */
   const float* term_noise_u187;
-  uint64_t* fused_ws;             /* hl_fused_workspace_bytes(N) bytes, zeroed ONCE at allocation */
+  uint64_t* fused_ws;             /* hl_fused_workspace_bytes(N) bytes, zeroed ONCE at allocation; also the tile
+                                   * ticket of the persistent fused kernel (NULL => the tiled fallback kernel runs) */
+  const float* height_min3f;      /* (rows-1,cols-1) fp32 = min3 * vertical_scale from hl_terrain_prepare_f32; may be
+                                   * NULL (then the fused step uses the tiled fallback kernel and height_min3) */
 } HlEnvBuffers;
 
 int hl_version(void);
@@ -186,6 +189,10 @@ int hl_pd_torque(const HlCfg* cfg, const float* actions, int64_t actions_row_str
  * shape (rows-1, cols-1); turns the three gathers of every height sample into one. */
 int hl_terrain_prepare(const int16_t* height_samples, int32_t rows, int32_t cols,
                        int16_t* height_min3_out, void* stream);
+/* Same table already in metres: out[px,py] = fp32(min3) * vertical_scale (the product `heights *
+ * vertical_scale` of LR:1355, rounded once like torch does), so a scan point is one fp32 gather. */
+int hl_terrain_prepare_f32(const int16_t* height_samples, int32_t rows, int32_t cols, float vertical_scale,
+                           float* height_min3f_out, void* stream);
 
 /* The fused post-physics step: every HL_ST_* stage for all envs in ONE kernel
  * (LeggedRobot.post_physics_step LR:178-247 minus the RNG/PhysX-driven calls, plus the obs clip

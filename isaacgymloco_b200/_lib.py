@@ -28,7 +28,8 @@ class HlEnvBuffers(ctypes.Structure):
         "privileged_obs_buf", "noise_u45", "noise_u187")] + [
         ("philox_seed", c_uint64), ("philox_offset", c_uint64), ("height_idx_out", _vp),
         ("base_height_out", _vp), ("reset_ids_out", _vp), ("n_reset_out", _vp), ("term_priv_out", _vp),
-        ("term_amp_out", _vp), ("term_noise_u45", _vp), ("term_noise_u187", _vp), ("fused_ws", _vp)]
+        ("term_amp_out", _vp), ("term_noise_u45", _vp), ("term_noise_u187", _vp), ("fused_ws", _vp),
+        ("height_min3f", _vp)]
 
 
 class HlTransition(ctypes.Structure):
@@ -61,6 +62,7 @@ EXPORTS = {
     "hl_sizeof_env_buffers": (c_int32, []),
     "hl_pd_torque": (c_int32, [POINTER(HlCfg), _vp, c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
     "hl_terrain_prepare": (c_int32, [_vp, c_int32, c_int32, _vp, _vp]),
+    "hl_terrain_prepare_f32": (c_int32, [_vp, c_int32, c_int32, c_float, _vp, _vp]),
     "hl_post_physics_fused": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), c_int64, _vp]),
     "hl_fused_workspace_bytes": (c_int64, [c_int64]),
     "hl_post_physics_stages": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), c_uint32, _vp, _vp, c_int64, _vp]),

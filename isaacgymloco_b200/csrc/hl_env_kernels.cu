@@ -164,6 +164,34 @@ extern "C" int hl_terrain_prepare(const int16_t* hs, int32_t rows, int32_t cols,
   return HL_OK;
 }
 
+__global__ void hl_terrain_min3f_kernel(const int16_t* __restrict__ h, int rows, int cols, float vs, float* __restrict__ out) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x, x = blockIdx.y;
+  if (y >= cols - 1 || x >= rows - 1) return;
+  const int a = h[(size_t)x * cols + y], b = h[(size_t)(x + 1) * cols + y], c = h[(size_t)x * cols + y + 1];
+  out[(size_t)x * (cols - 1) + y] = __fmul_rn((float)min(min(a, b), c), vs);   // LR:1355 `heights * vertical_scale`
+}
+extern "C" int hl_terrain_prepare_f32(const int16_t* hs, int32_t rows, int32_t cols, float vertical_scale, float* out, void* stream) {
+  HL_CHECK_ARG(hs && out && rows >= 2 && cols >= 2, "bad terrain");
+  dim3 grid((cols - 1 + 255) / 256, rows - 1);
+  hl_terrain_min3f_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(hs, rows, cols, vertical_scale, out);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}
+
+// SM count of the current device (cached per device id)
+static int device_sms() {
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int v = cache[dev];
+  if (!v) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cache[dev] = v;   // benign race: every thread computes the same value
+  }
+  return v;
+}
+
 // ============================================================================= shared pieces
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -1066,8 +1094,23 @@ __device__ __forceinline__ int scan_gather(const HlCfg& c, const int16_t* __rest
 #endif
 }
 
+// same cell arithmetic; the table already holds metres (hl_terrain_prepare_f32)
+template <bool CPU_MATH>
+__device__ __forceinline__ float scan_gather_f(const HlCfg& c, const float* __restrict__ min3f, int pitch, float qz, float qw,
+                                               float posx, float posy, float bx, float by) {
+  const float ty = 2.0f * __fmul_rn(qz, bx), tx = -2.0f * __fmul_rn(qz, by);
+  const float ay = __fmul_rn(qw, ty), cx = -__fmul_rn(qz, ty);
+  const float ax = __fmul_rn(qw, tx), cy = __fmul_rn(qz, tx);
+  const float rx = __fadd_rn(__fadd_rn(bx, ax), cx);
+  const float ry = __fadd_rn(__fadd_rn(by, ay), cy);
+  const int ix = cell32<CPU_MATH>(__fadd_rn(rx, posx), c.border_size, c.horizontal_scale, c.inv_horizontal_scale, c.terrain_rows - 2);
+  const int iy = cell32<CPU_MATH>(__fadd_rn(ry, posy), c.border_size, c.horizontal_scale, c.inv_horizontal_scale, c.terrain_cols - 2);
+  return __ldg(min3f + (unsigned)(ix * pitch + iy));
+}
+
 struct FusedArgs {
   int cf_stride, need_ldp, need_ltq, want_base;
+  int tma_ok;             // every dense slab of a full tile is 16-B aligned with a 16-B multiple size (n % 4 == 0, aligned bases)
   int sums_aligned;       // episode_sums rows are 16-B aligned per block (n % 4 == 0, base aligned)
   int compact;            // emit reset ids / count / terminal rows from this launch (decoupled look-back)
   int hist_clipped;       // obs history is known to be within +-clip_obs already (every step after the first)
@@ -1117,15 +1160,12 @@ struct FusedArgs {
 #undef FK_GENERIC
 #undef FK_COMPACT
 
+#include "hl_persist_kernel.inc"
+
 // Envs per CTA that minimises (waves x tile cost) for this shard on this device: a wave is
 // SMs x 3 resident CTAs; the cost of a tile is ~ a fixed part (loads, barriers) + its envs.
 static int pick_tile(int64_t n) {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
+  const int sms = device_sms();
   const char* fe = getenv("HL_FUSED_EPB");  // dev/test knob, read per call
   const int forced = fe ? atoi(fe) : 0;
   if (forced == 64 || forced == 52 || forced == 32) return forced;
@@ -1183,6 +1223,7 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
   fa.hist_clipped = (int)(b.flags & HL_BUF_HISTORY_CLIPPED);
   fa.compact = b.reset_ids_out != nullptr;
   HL_CHECK_ARG(!fa.compact || (b.n_reset_out && b.term_priv_out && b.fused_ws), "single-launch mode needs n_reset_out, term_priv_out, fused_ws");
+  fa.tma_ok = 0;
   {
     uint32_t x = (uint32_t)b.philox_seed, y = (uint32_t)(b.philox_seed >> 32);
     for (int r = 0; r < 10; ++r) {
@@ -1193,6 +1234,21 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
     }
   }
   const bool fast = P > 160 && P <= 192 && PB <= 64 && !hclip;
+  {
+    bool ok = (n % 4 == 0) && (!b.episode_sums || ((uintptr_t)b.episode_sums & 15) == 0);
+    fa.tma_ok = ok;
+  }
+  // HL_FUSED_IMPL=persist selects the persistent role-pipelined kernel (hl_persist_kernel.inc)
+  const char* impl = getenv("HL_FUSED_IMPL");
+  if (fast && impl && impl[0] == 'p') {
+    const int prc = pk::run(cfg, bufs, n, fa, cpu, device_sms(), st);
+    if (prc != HL_E_UNSUPPORTED) {
+      if (prc) return prc;
+      HL_CHECK_LAUNCH();
+      return HL_OK;
+    }
+  }
+  HL_CHECK_ARG(!fa.compact || b.fused_ws, "single-launch mode needs fused_ws");
   const int tile = pick_tile(n);
   int rc = HL_E_UNSUPPORTED;
   if (tile == 52) rc = fk52::run(cfg, bufs, n, fa, fast, cpu, st);

@@ -233,7 +233,8 @@ __device__ float hl_foot_clearance_terrain(const HlCfg& c, const HlEnvBuffers& b
 }
 
 // One `_reward_<name>()` value for this env (formulas: SURVEY.md A.4 / LR:1444-1770).
-__device__ float hl_eval_term(int id, const HlCfg& c, const HlEnvBuffers& b, const EnvView& v, EnvScalars& s) {
+// (forceinline: with a compile-time `id` the switch folds to the one case -- see reward_fast in hl_persist_kernel.inc)
+__device__ __forceinline__ float hl_eval_term(int id, const HlCfg& c, const HlEnvBuffers& b, const EnvView& v, EnvScalars& s) {
   float r = 0.0f;
   switch (id) {
     case T_action_rate:

@@ -125,6 +125,7 @@ class FusedLeggedRobot:
         self.termination_contact_indices = torch.tensor(cfg.termination_contact_indices, dtype=torch.long, device=dev)
         # terrain: the one-off min-of-3 table
         self._height_min3 = None
+        self._height_min3f = None
         # reset-id compaction + terminal rows (capacity N; counts live on the device)
         self._reset_ids = torch.zeros(n, dtype=torch.long, device=dev)
         self._n_reset = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -154,6 +155,10 @@ class FusedLeggedRobot:
             raise ValueError(f"height_samples is {rows}x{cols}, cfg expects {self.cfg_hot.terrain_shape}")
         self._height_min3 = torch.empty(rows - 1, cols - 1, dtype=torch.int16, device=self.device)
         L.check(L.lib.hl_terrain_prepare(L.ptr(self.height_samples), rows, cols, L.ptr(self._height_min3), L.stream()))
+        # the same table in metres (fp32): one gather per scan point in the persistent fused kernel
+        self._height_min3f = torch.empty(rows - 1, cols - 1, dtype=torch.float32, device=self.device)
+        L.check(L.lib.hl_terrain_prepare_f32(L.ptr(self.height_samples), rows, cols, float(self.cfg_hot.vertical_scale),
+                                             L.ptr(self._height_min3f), L.stream()))
 
     def set_noise_tensors(self, obs45=None, obs187=None, term45=None, term187=None):
         """Parity mode: the U[0,1) draws `torch.rand_like` would return at LR:394,400 (obs) and
@@ -209,6 +214,8 @@ class FusedLeggedRobot:
         b.contact_forces, b.rigid_body_states = p(self.contact_forces), p(self.rigid_body_states)
         b.height_samples = p(self.height_samples)
         b.height_min3 = p(self._height_min3)
+        b.height_min3f = p(self._height_min3f)
+        b.fused_ws = p(self._fused_ws)        # tile ticket of the persistent kernel (+ look-back states)
         b.actions, b.last_actions, b.last_last_actions = p(self.actions), p(self.last_actions), p(self.last_last_actions)
         b.last_dof_pos, b.last_dof_vel = p(self.last_dof_pos), p(self.last_dof_vel)
         b.torques, b.last_torques, b.last_root_vel = p(self.torques), p(self.last_torques), p(self.last_root_vel)
@@ -230,7 +237,6 @@ class FusedLeggedRobot:
             b.reset_ids_out, b.n_reset_out = p(self._reset_ids), p(self._n_reset)
             b.term_priv_out, b.term_amp_out = p(self._term_priv), p(self._term_amp)
             b.term_noise_u45, b.term_noise_u187 = p(self._noise.get("term45")), p(self._noise.get("term187"))
-            b.fused_ws = p(self._fused_ws)
         self._bufs = b
         return b
 

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(raw, name), f"{name} declared in include/himloco_b200.h but not exported"
     assert declared == set(L.EXPORTS), (declared ^ set(L.EXPORTS))
-    assert L.lib.hl_version() == 100
+    assert L.lib.hl_version() == 101
     assert L.lib.hl_sizeof_cfg() == ctypes.sizeof(L.HlCfg)
     assert L.lib.hl_sizeof_env_buffers() == ctypes.sizeof(L.HlEnvBuffers)
 
