@@ -1105,11 +1105,16 @@ __device__ __forceinline__ float scan_gather_f(const HlCfg& c, const float* __re
   const float ry = __fadd_rn(__fadd_rn(by, ay), cy);
   const int ix = cell32<CPU_MATH>(__fadd_rn(rx, posx), c.border_size, c.horizontal_scale, c.inv_horizontal_scale, c.terrain_rows - 2);
   const int iy = cell32<CPU_MATH>(__fadd_rn(ry, posy), c.border_size, c.horizontal_scale, c.inv_horizontal_scale, c.terrain_cols - 2);
+#ifdef HL_PKX_NO_GATHER
+  return (float)(ix + iy);
+#else
   return __ldg(min3f + (unsigned)(ix * pitch + iy));
+#endif
 }
 
 struct FusedArgs {
   int cf_stride, need_ldp, need_ltq, want_base;
+  int hist_pf;            // bulk-prefetch the tile's obs-history slab into L2 (obs_buf_in 16-B aligned)
   int tma_ok;             // every dense slab of a full tile is 16-B aligned with a 16-B multiple size (n % 4 == 0, aligned bases)
   int sums_aligned;       // episode_sums rows are 16-B aligned per block (n % 4 == 0, base aligned)
   int compact;            // emit reset ids / count / terminal rows from this launch (decoupled look-back)
@@ -1224,6 +1229,7 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
   fa.compact = b.reset_ids_out != nullptr;
   HL_CHECK_ARG(!fa.compact || (b.n_reset_out && b.term_priv_out && b.fused_ws), "single-launch mode needs n_reset_out, term_priv_out, fused_ws");
   fa.tma_ok = 0;
+  fa.hist_pf = 0;
   {
     uint32_t x = (uint32_t)b.philox_seed, y = (uint32_t)(b.philox_seed >> 32);
     for (int r = 0; r < 10; ++r) {
@@ -1237,6 +1243,8 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
   {
     bool ok = (n % 4 == 0) && (!b.episode_sums || ((uintptr_t)b.episode_sums & 15) == 0);
     fa.tma_ok = ok;
+    const char* pf = getenv("HL_PK_HIST_PF");   // experiment knob
+    fa.hist_pf = (((uintptr_t)b.obs_buf_in & 15) == 0) && !(pf && pf[0] == '0');
   }
   // HL_FUSED_IMPL=persist selects the persistent role-pipelined kernel (hl_persist_kernel.inc)
   const char* impl = getenv("HL_FUSED_IMPL");
@@ -1249,11 +1257,20 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
     }
   }
   HL_CHECK_ARG(!fa.compact || b.fused_ws, "single-launch mode needs fused_ws");
+  unsigned long long rmask = 0ull;   // active reward terms as a bit set (0 when not in sorted order: the generic loop keeps the caller's order)
+  for (int k = 0; k < cfg->n_terms; ++k) {
+    if (cfg->term_id[k] < 0 || cfg->term_id[k] >= T_COUNT || (k > 0 && cfg->term_id[k] <= cfg->term_id[k - 1])) {
+      rmask = 0ull;
+      break;
+    }
+    rmask |= 1ull << cfg->term_id[k];
+  }
+  { const char* g = getenv("HL_FUSED_GENERIC_REWARD"); if (g && g[0] == '1') rmask = 0ull; }   // A/B knob
   const int tile = pick_tile(n);
   int rc = HL_E_UNSUPPORTED;
-  if (tile == 52) rc = fk52::run(cfg, bufs, n, fa, fast, cpu, st);
-  else if (tile == 32) rc = fk32::run(cfg, bufs, n, fa, fast, cpu, st);
-  if (rc == HL_E_UNSUPPORTED) rc = fk64::run(cfg, bufs, n, fa, fast, cpu, st);
+  if (tile == 52) rc = fk52::run(cfg, bufs, n, fa, fast, cpu, rmask, st);
+  else if (tile == 32) rc = fk32::run(cfg, bufs, n, fa, fast, cpu, rmask, st);
+  if (rc == HL_E_UNSUPPORTED) rc = fk64::run(cfg, bufs, n, fa, fast, cpu, rmask, st);
   if (rc) return rc;
   HL_CHECK_LAUNCH();
   return HL_OK;

@@ -407,6 +407,117 @@ __device__ __forceinline__ float hl_compute_reward(const HlCfg& c, const HlEnvBu
   return rew;
 }
 
+__device__ __forceinline__ float4 hl_lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// ----------------------------------------------------------------------------- compile-time reward lists
+__host__ __device__ constexpr unsigned long long hl_tbit(int t) { return 1ull << t; }
+constexpr unsigned long long HL_MASK_COMMON =
+    hl_tbit(T_action_rate) | hl_tbit(T_ang_vel_xy) | hl_tbit(T_base_height) | hl_tbit(T_calf_pose) | hl_tbit(T_dof_acc) | hl_tbit(T_feet_air_time) |
+    hl_tbit(T_feet_contact_forces) | hl_tbit(T_feet_slide) | hl_tbit(T_hip_pos) | hl_tbit(T_joint_power) | hl_tbit(T_lin_vel_z) |
+    hl_tbit(T_orientation) | hl_tbit(T_stand_still) | hl_tbit(T_stuck) | hl_tbit(T_thigh_pose) | hl_tbit(T_torques) | hl_tbit(T_tracking_ang_vel) |
+    hl_tbit(T_tracking_lin_vel);
+// aliengo flat / AMP (aliengo_config.py:217-256): 21 terms
+constexpr unsigned long long HL_MASK_FLAT = HL_MASK_COMMON | hl_tbit(T_feet_mirror) | hl_tbit(T_foot_clearance_base) | hl_tbit(T_smoothness);
+// aliengo_stairs (aliengo_stairs_config.py:171-210): 20 terms (+ termination, added after the loop)
+constexpr unsigned long long HL_MASK_STAIRS = HL_MASK_COMMON | hl_tbit(T_collision) | hl_tbit(T_feet_stumble);
+__host__ __device__ constexpr int hl_popc64(unsigned long long x) { int c = 0; while (x) { x &= x - 1; ++c; } return c; }
+
+// compute_reward() (LR:363-380) for one env with the active terms known at compile time: no
+// dispatch, the per-DOF terms share one pass over the rows (128-bit shared-memory loads), the rest is
+// hl_eval_term with a constant id.  Same per-term op order as hl_eval_term; same alphabetical
+// accumulation.  `es` = this env's column of the (R, N) episode sums (row stride n) or NULL: each scaled term
+// is added by a fire-and-forget red.global.add.f32 -- one IEEE add per element per step by a single thread, so the
+// result is the same `sum += term` (LR:371) without a load, a register or a wait.
+template <unsigned long long M>
+__device__ __forceinline__ float hl_reward_fast(const HlCfg& c, const HlEnvBuffers& b, const EnvView& v, EnvScalars& s, float* es, long long n) {
+#define HAS(t) ((M >> (t)) & 1ull)
+  float a_rate = 0.f, a_acc = 0.f, a_pow = 0.f, a_smooth = 0.f, a_tq = 0.f, a_pose0 = 0.f, a_pose1 = 0.f, a_pose2 = 0.f, a_stand = 0.f;
+  {
+    const float inv_dt = 1.0f / c.dt;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      const float4 d0 = hl_lds4(v.dof + 8 * g), d1 = hl_lds4(v.dof + 8 * g + 4);
+      const float q[4] = {d0.x, d0.z, d1.x, d1.z}, qd[4] = {d0.y, d0.w, d1.y, d1.w};
+      float a[4] = {0.f, 0.f, 0.f, 0.f}, la[4] = {0.f, 0.f, 0.f, 0.f}, lla[4] = {0.f, 0.f, 0.f, 0.f}, lv[4] = {0.f, 0.f, 0.f, 0.f},
+            tq[4] = {0.f, 0.f, 0.f, 0.f};
+      if (HAS(T_action_rate) || HAS(T_smoothness)) {
+        const float4 x = hl_lds4(v.act + 4 * g), y = hl_lds4(v.lact + 4 * g);
+        a[0] = x.x; a[1] = x.y; a[2] = x.z; a[3] = x.w;
+        la[0] = y.x; la[1] = y.y; la[2] = y.z; la[3] = y.w;
+      }
+      if (HAS(T_smoothness)) {
+        const float4 x = hl_lds4(v.llact + 4 * g);
+        lla[0] = x.x; lla[1] = x.y; lla[2] = x.z; lla[3] = x.w;
+      }
+      if (HAS(T_dof_acc)) {
+        const float4 x = hl_lds4(v.ldv + 4 * g);
+        lv[0] = x.x; lv[1] = x.y; lv[2] = x.z; lv[3] = x.w;
+      }
+      if (HAS(T_joint_power) || HAS(T_torques)) {
+        const float4 x = hl_lds4(v.tq + 4 * g);
+        tq[0] = x.x; tq[1] = x.y; tq[2] = x.z; tq[3] = x.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = 4 * g + i;
+        if (HAS(T_action_rate)) a_rate += hl_sq(la[i] - a[i]);
+        if (HAS(T_dof_acc)) a_acc += hl_sq((lv[i] - qd[i]) * inv_dt);
+        if (HAS(T_joint_power)) a_pow += fabsf(qd[i]) * fabsf(tq[i]);
+        if (HAS(T_smoothness)) a_smooth += hl_sq(a[i] - la[i] - la[i] + lla[i]);
+        if (HAS(T_torques)) a_tq += hl_sq(tq[i]);
+        const float dev = fabsf(q[i] - c.default_dof_pos[d]);
+        if (HAS(T_stand_still) || HAS(T_stand_nice)) a_stand += dev;
+        if (d % 3 == 0) { if (HAS(T_hip_pos) || HAS(T_hip_pos_up)) a_pose0 += dev; }
+        else if (d % 3 == 1) { if (HAS(T_thigh_pose) || HAS(T_thigh_pose_up)) a_pose1 += dev; }
+        else { if (HAS(T_calf_pose) || HAS(T_calf_pose_up)) a_pose2 += dev; }
+      }
+    }
+  }
+  float rew = 0.0f;
+#define EMIT(t, val)                                            \
+  if (HAS(t)) {                                                 \
+    constexpr int k_ = hl_popc64(M & (hl_tbit(t) - 1ull));            \
+    const float r_ = (val) * c.term_scale[k_];                  \
+    rew += r_;                                                  \
+    if (es) atomicAdd(es + (long long)k_ * n, r_);              \
+  }
+#define EVAL(t) EMIT(t, hl_eval_term(t, c, b, v, s))
+  EMIT(T_action_rate, a_rate)
+  EVAL(T_ang_vel_xy) EVAL(T_ang_vel_xy_up) EVAL(T_base_height) EVAL(T_base_height_up)
+  EMIT(T_calf_pose, a_pose2)
+  EMIT(T_calf_pose_up, a_pose2 * hl_up(s))
+  EVAL(T_collision) EVAL(T_collision_up)
+  EMIT(T_dof_acc, a_acc)
+  EVAL(T_dof_pos_dif) EVAL(T_dof_pos_limits) EVAL(T_dof_vel) EVAL(T_dof_vel_limits) EVAL(T_feet_air_time)
+  EVAL(T_feet_contact_forces) EVAL(T_feet_mirror) EVAL(T_feet_mirror_up) EVAL(T_feet_slide) EVAL(T_feet_slide_up)
+  EVAL(T_feet_stumble) EVAL(T_feet_stumble_up) EVAL(T_foot_clearance_base) EVAL(T_foot_clearance_base_up)
+  EVAL(T_foot_clearance_terrain) EVAL(T_foot_clearance_terrain_up) EVAL(T_has_contact) EVAL(T_hip_action_magnitude)
+  EMIT(T_hip_pos, a_pose0)
+  EMIT(T_hip_pos_up, a_pose0 * hl_up(s))
+  EMIT(T_joint_power, a_pow)
+  EVAL(T_lin_vel_z) EVAL(T_lin_vel_z_up) EVAL(T_orientation) EVAL(T_orientation_up) EVAL(T_power) EVAL(T_power_distribution)
+  EMIT(T_smoothness, a_smooth)
+  EMIT(T_stand_nice, a_stand * (hl_cmd_norm(s) < 0.1f ? 1.0f : 0.0f) * (1.0f - s.pg[2]))
+  EMIT(T_stand_still, a_stand * (hl_cmd_norm(s) < 0.1f ? 1.0f : 0.0f))
+  EVAL(T_stuck)
+  EMIT(T_thigh_pose, a_pose1)
+  EMIT(T_thigh_pose_up, a_pose1 * hl_up(s))
+  EVAL(T_torque_limits)
+  EMIT(T_torques, a_tq)
+  EVAL(T_torques_dif) EVAL(T_torques_distribution) EVAL(T_tracking_ang_vel) EVAL(T_tracking_lin_vel) EVAL(T_upward)
+#undef EVAL
+#undef EMIT
+#undef HAS
+  if (c.only_positive_rewards) rew = fmaxf(rew, 0.0f);
+  if (c.has_termination_term) {
+    const float r = ((s.reset && !s.time_out) ? 1.0f : 0.0f) * c.termination_scale;
+    rew += r;
+    if (es) atomicAdd(es + (long long)hl_popc64(M) * n, r);
+  }
+  return rew;
+}
+
+
 __device__ __forceinline__ bool hl_needs_base_height(const HlCfg& c) {
   bool need = false;
   for (int k = 0; k < c.n_terms; ++k) need |= (c.term_id[k] == T_base_height) | (c.term_id[k] == T_base_height_up);
