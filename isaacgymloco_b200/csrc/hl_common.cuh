@@ -59,6 +59,9 @@ static inline void hl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size
   cudaLaunchKernelEx(&lc, kern, static_cast<KArgs>(args)...);   // errors surface in HL_CHECK_LAUNCH
 }
 
+// look-back state of a CTA / tile in the ordered reset-id compaction: epoch << 32 | flag << 30 | value
+constexpr unsigned long long HL_LB_AGG = 1ull << 30, HL_LB_PREFIX = 2ull << 30, HL_LB_VALUE = (1ull << 30) - 1ull;
+
 // ----------------------------------------------------------------------------- reward term ids
 // sorted() order of the 51 unique `_reward_*` names (legged_robot.py:1444-1770); mirrored by
 // isaacgymloco_b200/config.py::REWARD_TERMS.

@@ -762,10 +762,16 @@ __global__ void __launch_bounds__(256) hl_select_terminal_kernel(HlCfg c, HlEnvB
   __shared__ int s_local[SEL_ENVS];  // local env offsets of this CTA's reset envs, ascending
   hl_pdl_enter();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const unsigned vb = blockIdx.x, nblocks = gridDim.x;
+  const unsigned nblocks = gridDim.x;
   unsigned* ctrl = reinterpret_cast<unsigned*>(ws);
   volatile unsigned long long* state = reinterpret_cast<volatile unsigned long long*>(ws) + 2;
-  if (tid == 0) s_epoch = *reinterpret_cast<volatile unsigned*>(ctrl + 2) + 1u;
+  __shared__ unsigned s_vb;
+  if (tid == 0) {   // virtual block id by ticket: a CTA only ever waits on CTAs that have already started
+    s_vb = atomicAdd(ctrl, 1u);
+    s_epoch = *reinterpret_cast<volatile unsigned*>(ctrl + 2) + 1u;
+  }
+  __syncthreads();
+  const unsigned vb = s_vb;
   const long long e0 = (long long)vb * SEL_ENVS;
   // one flag per thread
   const long long off = e0 + tid;
@@ -785,7 +791,7 @@ __global__ void __launch_bounds__(256) hl_select_terminal_kernel(HlCfg c, HlEnvB
     int tot = 0;
     for (int w = 0; w < 8; ++w) tot += warp_tot[w];
     s_total = tot;
-    state[vb] = ((unsigned long long)s_epoch << 32) | (unsigned)tot;  // publish early
+    state[vb] = ((unsigned long long)s_epoch << 32) | HL_LB_AGG | (unsigned long long)(unsigned)tot;  // publish early
     __threadfence();
   }
   int pos = wbase + incl - cnt;
@@ -800,27 +806,29 @@ __global__ void __launch_bounds__(256) hl_select_terminal_kernel(HlCfg c, HlEnvB
     hl_stage_rows_env(st, b, e0 + s_local[wid], lane, v);
     staged = true;
   }
-  if (wid == 0) {  // exclusive prefix = sum of the counts of all lower CTAs
+  if (wid == 0) {  // exclusive prefix: nearest earlier CTA with an inclusive prefix + the aggregates in between
     const unsigned ep = s_epoch;
     int acc = 0;
-    for (unsigned base = 0; base < vb; base += 32 * 8) {
-      unsigned long long w[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const unsigned j = base + u * 32 + lane;
-        w[u] = j < vb ? state[j] : ((unsigned long long)ep << 32);
+    long long t = (long long)vb - 1;
+    while (t >= 0) {
+      const long long idx = t - lane;
+      unsigned long long w = ((unsigned long long)ep << 32) | HL_LB_PREFIX;
+      if (idx >= 0) {
+        w = state[idx];
+        while ((unsigned)(w >> 32) != ep) w = state[idx];
       }
+      const unsigned pm = __ballot_sync(0xffffffffu, (w & HL_LB_PREFIX) != 0ull);
+      const int first = pm ? (__ffs(pm) - 1) : 31;
+      int val = lane <= first ? (int)(w & HL_LB_VALUE) : 0;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const unsigned j = base + u * 32 + lane;
-        while ((unsigned)(w[u] >> 32) != ep) w[u] = state[j];
-        acc += (int)(unsigned)w[u];
-      }
+      for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+      acc += val;
+      if (pm) break;
+      t -= 32;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
       s_excl = acc;
+      state[vb] = ((unsigned long long)ep << 32) | HL_LB_PREFIX | (unsigned long long)(unsigned)(acc + s_total);
       if (vb == nblocks - 1) *count_out = acc + s_total;
     }
   }
@@ -888,6 +896,7 @@ __global__ void __launch_bounds__(256) hl_select_terminal_kernel(HlCfg c, HlEnvB
   if (tid == 0) {  // last CTA re-arms the workspace (graph safe)
     __threadfence();
     if (atomicAdd(ctrl + 1, 1u) == nblocks - 1) {
+      ctrl[0] = 0u;
       ctrl[1] = 0u;
       ctrl[2] = s_epoch;
       __threadfence();
@@ -1146,7 +1155,7 @@ struct FusedArgs {
 #define FK_THREADS 288
 #endif
 #define FK_GENERIC 0
-#define FK_COMPACT 0
+#define FK_COMPACT 1
 #include "hl_fused_kernel.inc"
 #undef FK_NS
 #undef FK_EPB
@@ -1186,7 +1195,7 @@ static int pick_tile(int64_t n) {
   return best;
 }
 
-extern "C" int64_t hl_fused_workspace_bytes(int64_t n) { return (int64_t)(((n + 32 - 1) / 32) + 2) * 8; }  // sized for the smallest tile
+extern "C" int64_t hl_fused_workspace_bytes(int64_t n) { return (int64_t)(((n + 16 - 1) / 16) + 2) * 8; }  // sized for tiles of >= 16 envs
 
 extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, void* stream) {
   if (int r = check_cfg(cfg, bufs)) return r;

@@ -18,6 +18,7 @@ Fused step (post_physics_step):
     hl_post_reset_fixup        re-scan + obs slot 0 + roll for the reset envs       LR:232-241,332-333
 """
 import ctypes
+import os
 from typing import Callable, Dict, Optional
 
 import torch
@@ -137,6 +138,8 @@ class FusedLeggedRobot:
         # ids + terminal rows straight from the fused kernel: wins in the launch-bound small-N regime,
         # costs more than the separate compaction launch at large N (measured)
         self.single_launch = n <= 16384
+        if os.environ.get("HL_SINGLE_LAUNCH") in ("0", "1"):      # A/B knob
+            self.single_launch = os.environ["HL_SINGLE_LAUNCH"] == "1"
         # noise: Philox by default; parity tests install pre-drawn tensors
         self._noise = {}
         self._philox_seed = int(seed)
