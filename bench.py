@@ -153,6 +153,11 @@ class Workload:
         from isaacgymloco_b200.rollout_storage import HIMRolloutStorage
         self.envs, self.t_len, self.world, self.device = envs, t_len, world, device
         self.cfg = C.aliengo("flat", num_envs=envs * world, env_id_offset=rank * envs)
+        # the torch-RNG / PhysX-facing interval hooks (pushes, disturbances, the host-side command curriculum) are
+        # outside the path; everything else of post_physics_step runs, reset_idx included
+        self.cfg.reset.push_robots = False
+        self.cfg.reset.disturbance = False
+        self.cfg.reset.commands_curriculum = False
         hf = S.make_terrain(self.cfg, seed=1)
         state = S.make_state(self.cfg, envs, hf, seed=seed + rank, env_id_offset=rank * envs)
         self.host_state = state
@@ -184,10 +189,10 @@ class Workload:
             env._fused_event_hook = hook
         else:
             env._fused_event_hook = None
-        env.fused_pre_reset()                          # fused kernel, reset-id compaction, terminal rows
-        env.fused_post_reset(with_reset_zero=True)     # no torch reset_idx in the replay loop
-        env.common_step_counter += 1
-        self.launches += env.cfg_hot.decimation + (2 if env.single_launch else 3)
+        # the whole of post_physics_step as one chain of launches, no host sync: pre-step command resampling, the fused
+        # kernel, reset ids + terminal rows, episode logging means, reset_idx (Philox re-draws) + post-reset fix-up
+        env.post_physics_step_device()
+        self.launches += env.cfg_hot.decimation + (4 if env.single_launch else 5)
 
     def rollout(self, time_fused=False, finish=True):
         for _ in range(self.t_len):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HL_VERSION 101
+#define HL_VERSION 102
 
 #define HL_OK 0
 #define HL_E_INVALID 1   /* bad argument / inconsistent config */
@@ -60,6 +60,7 @@ extern "C" {
 #define HL_ST_ROLL 0x400u        /* disturbance=0, last_* <- current            LR:235-241    */
 #define HL_ST_BASE_HEIGHT 0x800u /* base_height_out = _get_base_heights()       LR:1357-1398  */
 #define HL_ST_RESET_ZERO 0x1000u /* the RNG-free buffer resets of reset_idx     LR:323-329,350,361 */
+#define HL_ST_RESET_DRAW 0x2000u /* the state re-draws of reset_idx (needs HlReset) LR:301-320,336-341 */
 #define HL_ST_ALL_STEP (HL_ST_COUNTERS | HL_ST_FRAME | HL_ST_CONTACTS | HL_ST_HEADING | HL_ST_HEIGHTS | \
                         HL_ST_TERMINATION | HL_ST_REWARD | HL_ST_OBS | HL_ST_OBS_CLIP | HL_ST_ROLL)
 
@@ -238,6 +239,78 @@ int hl_select_and_terminal(const HlCfg* cfg, const HlEnvBuffers* bufs, const flo
  * = 0, LR:323-329,350,361) for callers whose reset_idx does not (synthetic replay, bench). */
 int hl_post_reset_fixup(const HlCfg* cfg, const HlEnvBuffers* bufs, const int64_t* env_ids,
                         const int32_t* n_ids_dev, int32_t with_reset_zero, int64_t n_envs, void* stream);
+
+/* reset_idx's state re-draws in the kernel chain: _update_terrain_curriculum
+ * (LR:845-866), _reset_dofs (LR:690-716), _reset_root_states (LR:718-820), _resample_commands (LR:634-656) and
+ * the Kp / Kd / motor-strength factor re-draws (LR:336-341), one warp per reset env.  Every `torch_rand_float(lo, hi)`
+ * of the reference is `lo + (hi - lo) * u` with u from a per-env vector of HL_RESET_NU uniforms: pre-drawn
+ * (`uniforms`, parity mode: rows indexed by env id) or Philox4x32-10 stream 3 keyed by (seed, offset, global env id)
+ * -- statistically, not bitwise, the reference's torch stream.  The PhysX setters the reference calls afterwards
+ * (set_dof_state_tensor_indexed, set_actor_root_state_tensor_indexed) stay with the caller: the kernel writes the
+ * same rows of the same tensors.  Column map of the uniforms:
+ *   0-11 dof_pos ratio | 12-23 dof_vel | 24-26 base x,y,z | 27-29 roll,pitch,yaw | 30-35 base lin/ang vel |
+ *   36 cmd vx | 37 cmd vy | 38 cmd heading (or yaw rate) | 39 cmd vx of a high-speed env | 40 Kp | 41 Kd |
+ *   42 motor strength | 43 random terrain level */
+#define HL_RESET_NU 44
+#define HL_RESET_DOFS 1u
+#define HL_RESET_ROOT 2u
+#define HL_RESET_COMMANDS 4u
+#define HL_RESET_FACTORS 8u
+#define HL_RESET_CURRICULUM 16u
+typedef struct HlReset {
+  int32_t struct_bytes;            /* sizeof(HlReset): ABI guard */
+  int32_t custom_origins;          /* LR:726 */
+  int32_t has_pos_range;           /* domain_rand.base_init_pos_range given (else xy in +-1 m, LR:746) */
+  int32_t has_rot_range;           /* domain_rand.base_init_rot_range given (LR:753) */
+  int32_t vel_range_is_dict;       /* base_init_vel_range: 0 = (lo, hi) for all six, 1 = per axis (LR:779-816) */
+  int32_t randomize_dof_pos;       /* dof_init_pos_ratio_range given (LR:698) */
+  int32_t randomize_dof_vel;       /* LR:707 */
+  int32_t randomize_kp, randomize_kd, randomize_motor_strength;   /* LR:336-341 */
+  int32_t heading_command;         /* LR:645 */
+  int32_t terrain_curriculum;      /* cfg.terrain.curriculum and init_done (LR:301,853) */
+  int32_t max_terrain_level;       /* LR:1235 */
+  int32_t n_terrain_types;         /* columns of terrain_origins */
+  int32_t parts;                   /* 0 = everything; else HL_RESET_* bits: only those parts (the individual reset hooks) */
+  int32_t pad_;
+  int64_t num_envs_global;         /* for the high-speed slice env_id < 0.2 * num_envs (LR:649) */
+  float base_init_state[13];       /* LR:1160-1161 */
+  float pos_range[6];              /* x lo,hi, y lo,hi, z lo,hi */
+  float rot_range[6];              /* roll, pitch, yaw lo,hi */
+  float vel_range[12];             /* tuple: [0],[1]; dict: x,y,z,roll,pitch,yaw lo,hi */
+  float dof_pos_ratio[2], dof_vel_range[2];
+  float kp_range[2], kd_range[2], motor_strength_range[2];
+  float cmd_lin_vel_x[2], cmd_lin_vel_y[2], cmd_ang_vel_yaw[2], cmd_heading[2];   /* self.command_ranges (they move with the curriculum) */
+  float high_vel_frac;             /* 0.2 */
+  float env_length, max_episode_length_s;   /* LR:858,860 */
+  /* device buffers the re-draws write (the env's own tensors) */
+  float* root_states;              /* (N,13) */
+  float* dof_state;                /* (N,12,2) */
+  float* commands;                 /* (N,4) */
+  float* env_origins;              /* (N,3) */
+  const float* terrain_origins;    /* (levels, types, 3) or NULL */
+  int64_t* terrain_levels;         /* (N,) */
+  const int64_t* terrain_types;    /* (N,) or NULL */
+  float* kp_factors;               /* (N,1) or NULL */
+  float* kd_factors;               /* (N,1) or NULL */
+  float* motor_strength_factors;   /* (N,1) or NULL */
+  const float* uniforms;           /* (N, HL_RESET_NU) pre-drawn U[0,1) or NULL => Philox stream 3 */
+} HlReset;
+int hl_sizeof_reset(void);
+/* reset_idx(env_ids) without the fix-up: curriculum, state re-draws, the RNG-free buffer resets (LR:323-329,361). */
+int hl_reset_idx(const HlCfg* cfg, const HlEnvBuffers* bufs, const HlReset* reset, const int64_t* env_ids,
+                 const int32_t* n_ids_dev, int64_t n_envs, void* stream);
+/* Only the re-draws selected by reset->parts, no buffer zeroing: the individual hooks _reset_dofs(env_ids) /
+ * _reset_root_states(env_ids) called on their own. */
+int hl_reset_draw(const HlCfg* cfg, const HlEnvBuffers* bufs, const HlReset* reset, const int64_t* env_ids,
+                  const int32_t* n_ids_dev, int64_t n_envs, void* stream);
+/* The same followed by hl_post_reset_fixup's work for the same env, in ONE launch (what post_physics_step runs). */
+int hl_reset_and_fixup(const HlCfg* cfg, const HlEnvBuffers* bufs, const HlReset* reset, const int64_t* env_ids,
+                       const int32_t* n_ids_dev, int64_t n_envs, void* stream);
+/* _resample_commands(env_ids) (LR:634-656).  env_ids NULL: the envs whose episode_length_buf + 1 is a multiple of
+ * `interval` -- the pre-step resampling of _post_physics_step_callback (LR:612-613), evaluated before the fused step
+ * increments the counter.  Uniform columns 36-39 (Philox stream 2 for the pre-step form). */
+int hl_resample_commands(const HlCfg* cfg, const HlEnvBuffers* bufs, const HlReset* reset, const int64_t* env_ids,
+                         const int32_t* n_ids_dev, int64_t interval, int64_t n_envs, void* stream);
 
 /* ReplayBuffer.insert(states, next_states) -- rsl_rl/rsl_rl/storage/replay_buffer.py:52-68: row r of
  * both (n_rows, width) inputs is written to ring row (step + r) mod buffer_rows; when more than

@@ -11,7 +11,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_uin
 import torch
 
 from . import build as _build
-from .config import HlCfg
+from .config import HlCfg, HlReset
 
 _vp = c_void_p
 
@@ -53,7 +53,10 @@ class HlGatherFields(ctypes.Structure):
 # stage bits (include/himloco_b200.h)
 ST_COUNTERS, ST_FRAME, ST_CONTACTS, ST_HEADING, ST_HEIGHTS = 0x001, 0x002, 0x004, 0x008, 0x010
 ST_TERMINATION, ST_REWARD, ST_OBS, ST_OBS_NOSHIFT, ST_OBS_CLIP = 0x020, 0x040, 0x080, 0x100, 0x200
-ST_ROLL, ST_BASE_HEIGHT, ST_RESET_ZERO = 0x400, 0x800, 0x1000
+ST_ROLL, ST_BASE_HEIGHT, ST_RESET_ZERO, ST_RESET_DRAW = 0x400, 0x800, 0x1000, 0x2000
+
+# bits of HlReset.parts (include/himloco_b200.h)
+RESET_DOFS, RESET_ROOT, RESET_COMMANDS, RESET_FACTORS, RESET_CURRICULUM = 1, 2, 4, 8, 16
 
 EXPORTS = {
     "hl_version": (c_int32, []),
@@ -72,6 +75,11 @@ EXPORTS = {
     "hl_select_terminal_workspace_bytes": (c_int64, [c_int64]),
     "hl_select_and_terminal": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
     "hl_post_reset_fixup": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), _vp, _vp, c_int32, c_int64, _vp]),
+    "hl_sizeof_reset": (c_int32, []),
+    "hl_reset_idx": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), POINTER(HlReset), _vp, _vp, c_int64, _vp]),
+    "hl_reset_draw": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), POINTER(HlReset), _vp, _vp, c_int64, _vp]),
+    "hl_reset_and_fixup": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), POINTER(HlReset), _vp, _vp, c_int64, _vp]),
+    "hl_resample_commands": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), POINTER(HlReset), _vp, _vp, c_int64, c_int64, _vp]),
     "hl_episode_means": (c_int32, [_vp, _vp, _vp, _vp, c_int32, c_int64, c_float, c_int32, _vp, _vp]),
     "hl_amp_observations": (c_int32, [_vp, _vp, _vp, _vp, c_int64, _vp]),
     "hl_gae_scan": (c_int32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, c_int32, c_int64, c_float, c_float, _vp]),
@@ -105,6 +113,8 @@ def _load():
     if lib.hl_sizeof_env_buffers() != ctypes.sizeof(HlEnvBuffers):
         raise ImportError(f"HlEnvBuffers layout mismatch: python {ctypes.sizeof(HlEnvBuffers)} vs "
                           f"library {lib.hl_sizeof_env_buffers()}")
+    if lib.hl_sizeof_reset() != ctypes.sizeof(HlReset):
+        raise ImportError(f"HlReset layout mismatch: python {ctypes.sizeof(HlReset)} vs library {lib.hl_sizeof_reset()}")
     if lib.hl_sizeof_gather_fields() != ctypes.sizeof(HlGatherFields):
         raise ImportError("HlGatherFields layout mismatch")
     if lib.hl_sizeof_transition() != ctypes.sizeof(HlTransition):

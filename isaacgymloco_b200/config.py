@@ -130,8 +130,69 @@ _BASE_POINTS_Y = [-0.2, -0.15, -0.1, -0.05, 0., 0.05, 0.1, 0.15, 0.2]   # legged
 _BASE_POINTS_X = [-0.15, -0.1, -0.05, 0., 0.05, 0.1, 0.15]              # legged_robot.py:1309
 
 
+RESET_NU = 44   # include/himloco_b200.h: HL_RESET_NU
+
+
+class HlReset(ctypes.Structure):
+    """Mirror of `struct HlReset` (keep field order identical to the header)."""
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "struct_bytes", "custom_origins", "has_pos_range", "has_rot_range", "vel_range_is_dict", "randomize_dof_pos",
+        "randomize_dof_vel", "randomize_kp", "randomize_kd", "randomize_motor_strength", "heading_command",
+        "terrain_curriculum", "max_terrain_level", "n_terrain_types", "parts", "pad_")] + [
+        ("num_envs_global", ctypes.c_int64),
+        ("base_init_state", ctypes.c_float * 13), ("pos_range", ctypes.c_float * 6), ("rot_range", ctypes.c_float * 6),
+        ("vel_range", ctypes.c_float * 12), ("dof_pos_ratio", ctypes.c_float * 2), ("dof_vel_range", ctypes.c_float * 2),
+        ("kp_range", ctypes.c_float * 2), ("kd_range", ctypes.c_float * 2), ("motor_strength_range", ctypes.c_float * 2),
+        ("cmd_lin_vel_x", ctypes.c_float * 2), ("cmd_lin_vel_y", ctypes.c_float * 2), ("cmd_ang_vel_yaw", ctypes.c_float * 2),
+        ("cmd_heading", ctypes.c_float * 2), ("high_vel_frac", ctypes.c_float), ("env_length", ctypes.c_float),
+        ("max_episode_length_s", ctypes.c_float)] + [(n, ctypes.c_void_p) for n in (
+        "root_states", "dof_state", "commands", "env_origins", "terrain_origins", "terrain_levels", "terrain_types",
+        "kp_factors", "kd_factors", "motor_strength_factors", "uniforms")]
+
+
 def _f32(x) -> float:
     return float(np.float32(x))
+
+
+@dataclass
+class ResetCfg:
+    """reset_idx / command-resampling / domain-rand settings (aliengo_config.py:102-215; the reference keeps
+    them in cfg.init_state, cfg.commands and cfg.domain_rand).  `None` ranges = the reference's
+    `hasattr(...)` / `getattr(..., None)` fallbacks (legged_robot.py:698,707,728,753,774)."""
+    base_init_state: List[float] = field(default_factory=lambda: [0., 0., 0.50, 0., 0., 0., 1., 0., 0., 0., 0., 0., 0.])
+    base_init_pos_range: Optional[Dict[str, List[float]]] = field(
+        default_factory=lambda: dict(x=[-1.0, 1.0], y=[-1.0, 1.0], z=[0.0, 0.05]))
+    base_init_rot_range: Optional[Dict[str, List[float]]] = field(
+        default_factory=lambda: dict(roll=[-0.2, 0.2], pitch=[-0.2, 0.2], yaw=[-0.0, 0.0]))
+    base_init_vel_range: object = field(
+        default_factory=lambda: dict(x=[-0.5, 0.5], y=[-0.5, 0.5], z=[-0.5, 0.5], roll=[-0.5, 0.5], pitch=[-0.5, 0.5], yaw=[-0.5, 0.5]))
+    dof_init_pos_ratio_range: Optional[List[float]] = field(default_factory=lambda: [0.5, 1.5])
+    randomize_dof_vel: bool = True
+    # the cfg file says `dof_init_vel_range = [-0.1, 0.1]` (aliengo_config.py:201) but legged_robot.py:708 reads
+    # `init_dof_vel_range`, which does not exist => the reference really draws from its fallback [-1, 1]
+    dof_init_vel_range: List[float] = field(default_factory=lambda: [-1.0, 1.0])
+    max_forward_curriculum: float = 1.5   # aliengo_config.py:104-106
+    max_backward_curriculum: float = 1.0
+    max_lat_curriculum: float = 1.0
+    randomize_kp: bool = True
+    kp_range: List[float] = field(default_factory=lambda: [0.9, 1.1])
+    randomize_kd: bool = True
+    kd_range: List[float] = field(default_factory=lambda: [0.9, 1.1])
+    randomize_motor_strength: bool = True
+    motor_strength_range: List[float] = field(default_factory=lambda: [0.9, 1.1])
+    # commands (aliengo_config.py:102-115); the curriculum moves these at run time (legged_robot.py:868-880)
+    lin_vel_x: List[float] = field(default_factory=lambda: [-1.0, 1.0])
+    lin_vel_y: List[float] = field(default_factory=lambda: [-0.5, 0.5])
+    ang_vel_yaw: List[float] = field(default_factory=lambda: [-1.0, 1.0])
+    heading: List[float] = field(default_factory=lambda: [-math.pi, math.pi])
+    commands_curriculum: bool = True
+    terrain_curriculum: bool = True
+    # interval domain randomisation (legged_robot.py:627-632)
+    push_robots: bool = True
+    max_push_vel_xy: float = 1.0
+    disturbance: bool = True
+    disturbance_range: List[float] = field(default_factory=lambda: [-30.0, 30.0])
+    delay: bool = True                   # legged_robot.py:134-138
 
 
 @dataclass
@@ -215,6 +276,9 @@ class HotPathCfg:
     amp_task_reward_lerp: float = 0.3
     # numerics
     index_math: int = INDEX_MATH_TORCH_CUDA
+    # reset_idx / resampling / interval domain-rand (hooks and the in-kernel re-draws)
+    reset: ResetCfg = field(default_factory=ResetCfg)
+    using_amp: bool = False              # step() returns the 8-tuple of legged_robot.py:173-174
 
     # ----------------------------------------------------------------- derived (reference rules)
     @property
@@ -447,7 +511,8 @@ def aliengo(task: str = "flat", num_envs: int = 4096, **overrides) -> HotPathCfg
         sc["base_height"] = -10.0                      # aliengo_amp_config.py:226
         # aliengo_amp_config.py has no `termination` class: check_termination (LR:266-283) then keeps
         # only the contact and time-out clauses
-        cfg = HotPathCfg(num_envs=num_envs, reward_scales=sc, out_of_border=False, fall_down=False)
+        cfg = HotPathCfg(num_envs=num_envs, reward_scales=sc, out_of_border=False, fall_down=False, using_amp=True)
+        cfg.reset.max_forward_curriculum = 2.0          # aliengo_amp_config.py (commands.max_forward_curriculum)
     elif task == "stairs":
         cfg = HotPathCfg(
             num_envs=num_envs, reward_scales=dict(_STAIRS_SCALES), terrain_length=10.0,
@@ -460,6 +525,8 @@ def aliengo(task: str = "flat", num_envs: int = 4096, **overrides) -> HotPathCfg
         cfg = HotPathCfg(num_envs=num_envs, reward_scales=dict(_RECOVER_SCALES),
                          only_positive_rewards=True, heading_command=False,
                          terrain_proportions=[0.5, 0.5], termination_contact_indices=[])
+        cfg.reset.max_forward_curriculum = 2.0
+        cfg.reset.base_init_rot_range = dict(roll=[-3.14, 3.14], pitch=[-3.14, 3.14], yaw=[-3.14, 3.14])   # aliengo_recover_config.py
     else:
         raise ValueError(f"unknown task {task!r}")
     for k, v in overrides.items():
@@ -524,4 +591,23 @@ def from_reference_cfg(rc, num_envs: Optional[int] = None, sim_dt: float = 0.005
         push_interval_s=getattr(rc.domain_rand, "push_interval_s", 16),
         **idx,
     )
+    dr, init, cmd = rc.domain_rand, rc.init_state, rc.commands
+    g = lambda o, k, d=None: getattr(o, k, d)
+    cfg.reset = ResetCfg(
+        base_init_state=list(init.pos) + list(init.rot) + list(init.lin_vel) + list(init.ang_vel),
+        base_init_pos_range=g(dr, "base_init_pos_range"), base_init_rot_range=g(dr, "base_init_rot_range"),
+        base_init_vel_range=g(dr, "base_init_vel_range") if g(dr, "base_init_vel_range") is not None else (-0.5, 0.5),
+        dof_init_pos_ratio_range=g(dr, "dof_init_pos_ratio_range"), randomize_dof_vel=bool(g(dr, "randomize_dof_vel", False)),
+        dof_init_vel_range=list(g(dr, "init_dof_vel_range", [-1.0, 1.0])),        # sic: legged_robot.py:708 reads `init_dof_vel_range`
+        randomize_kp=bool(g(dr, "randomize_kp", False)), kp_range=list(g(dr, "kp_range", [1.0, 1.0])),
+        randomize_kd=bool(g(dr, "randomize_kd", False)), kd_range=list(g(dr, "kd_range", [1.0, 1.0])),
+        randomize_motor_strength=bool(g(dr, "randomize_motor_strength", False)),
+        motor_strength_range=list(g(dr, "motor_strength_range", [1.0, 1.0])),
+        lin_vel_x=list(cmd.ranges.lin_vel_x), lin_vel_y=list(cmd.ranges.lin_vel_y), ang_vel_yaw=list(cmd.ranges.ang_vel_yaw),
+        heading=list(cmd.ranges.heading), commands_curriculum=bool(g(cmd, "curriculum", False)),
+        terrain_curriculum=bool(g(t, "curriculum", False)), push_robots=bool(g(dr, "push_robots", False)),
+        max_push_vel_xy=float(g(dr, "max_push_vel_xy", 1.0)), disturbance=bool(g(dr, "disturbance", False)),
+        disturbance_range=list(g(dr, "disturbance_range", [-30.0, 30.0])), delay=bool(g(dr, "delay", False)),
+        max_forward_curriculum=float(g(cmd, "max_forward_curriculum", 1.5)),
+        max_backward_curriculum=float(g(cmd, "max_backward_curriculum", 1.0)), max_lat_curriculum=float(g(cmd, "max_lat_curriculum", 1.0)))
     return cfg

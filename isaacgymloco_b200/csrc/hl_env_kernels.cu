@@ -381,10 +381,150 @@ __device__ __forceinline__ void hl_stage_env(float* st, const HlCfg& c, const Hl
   v.ltq = st + WS_A + 72;
 }
 
+// ============================================================================= reset_idx re-draws
+// u[k] of one env: column k of its uniform vector (include/himloco_b200.h: HL_RESET_NU).  Philox mode: lane l
+// computes block l (four uniforms) of stream `stream`, keyed by (seed, offset, global env id); a shuffle hands
+// column k to every lane.
+struct ResetUniforms {
+  uint4 blk;
+  const float* row;   // pre-drawn row or nullptr
+  __device__ __forceinline__ void init(const HlEnvBuffers& b, const HlReset& r, long long e, unsigned long long genv, int lane, unsigned stream) {
+    row = r.uniforms ? r.uniforms + e * HL_RESET_NU : nullptr;
+    blk = make_uint4(0u, 0u, 0u, 0u);
+    if (!row && lane < (HL_RESET_NU + 3) / 4) blk = hl_noise_block(b.philox_seed, b.philox_offset, genv, (unsigned)lane, stream);
+  }
+  __device__ __forceinline__ float get(int k) const {   // warp-uniform k; every lane of the warp must call
+    const unsigned x = __shfl_sync(0xffffffffu, hl_pick(blk, k & 3), k >> 2);
+    return row ? row[k] : hl_u01(x);
+  }
+  __device__ __forceinline__ float range(int k, const float* lohi) const {   // torch_rand_float(lo, hi): (hi - lo) * u + lo
+    return (lohi[1] - lohi[0]) * get(k) + lohi[0];
+  }
+};
+
+// _resample_commands for one env (LR:634-656); lane 0 stores
+__device__ __forceinline__ void hl_resample_env(const HlReset& r, const ResetUniforms& ru, long long e, long long gid, int lane) {
+  float c0 = (1.0f - (-1.0f)) * ru.get(36) + (-1.0f);            // LR:641
+  float c1 = ru.range(37, r.cmd_lin_vel_y);                        // LR:642
+  const float c3 = ru.range(38, r.heading_command ? r.cmd_heading : r.cmd_ang_vel_yaw);   // LR:643-646
+  const float hv = ru.range(39, r.cmd_lin_vel_x);
+  if ((double)gid < (double)r.num_envs_global * (double)r.high_vel_frac) {   // LR:649-653 (env_ids < num_envs * 0.2)
+    c0 = hv;
+    c1 *= fabsf(c0) < 1.0f ? 1.0f : 0.0f;     // norm of a 1-vector
+  }
+  const float keep = sqrtf(c0 * c0 + c1 * c1) > 0.2f ? 1.0f : 0.0f;   // LR:656
+  c0 *= keep;
+  c1 *= keep;
+  if (lane == 0) {
+    r.commands[e * 4 + 0] = c0;
+    r.commands[e * 4 + 1] = c1;
+    r.commands[e * 4 + (r.heading_command ? 3 : 2)] = c3;
+  }
+}
+
+// reset_idx for env e, the part that draws: terrain curriculum, dofs, root state, commands, gain factors
+// (LR:301-320,336-341).  Warp-cooperative: lanes 0-11 own one dof each, lane 0 the scalars.
+__device__ __forceinline__ void hl_reset_draw_env(const HlCfg& c, const HlEnvBuffers& b, const HlReset& r, long long e, int lane) {
+  const long long gid = e + c.env_id_offset;
+  ResetUniforms ru;
+  ru.init(b, r, e, (unsigned long long)gid, lane, 3u);
+  const unsigned parts = r.parts ? (unsigned)r.parts : 0xffffffffu;
+  // ---- _update_terrain_curriculum (LR:845-866): pre-reset root position and commands
+  if ((parts & HL_RESET_CURRICULUM) && r.terrain_curriculum && r.terrain_origins && r.terrain_types) {
+    const float dx = r.root_states[e * 13 + 0] - r.env_origins[e * 3 + 0], dy = r.root_states[e * 13 + 1] - r.env_origins[e * 3 + 1];
+    const float dist = sqrtf(dx * dx + dy * dy);
+    const float cx = r.commands[e * 4 + 0], cy = r.commands[e * 4 + 1];
+    const bool up = dist > r.env_length / 2.0f;
+    const bool down = (dist < sqrtf(cx * cx + cy * cy) * r.max_episode_length_s * 0.5f) && !up;
+    long long lvl = r.terrain_levels[e] + (up ? 1 : 0) - (down ? 1 : 0);
+    const float ul = ru.get(43);
+    if (lvl >= r.max_terrain_level) {
+      long long rl = (long long)(ul * (float)r.max_terrain_level);   // torch.randint_like(levels, max_terrain_level)
+      lvl = rl < r.max_terrain_level ? rl : r.max_terrain_level - 1;
+    } else if (lvl < 0) {
+      lvl = 0;
+    }
+    __syncwarp();
+    if (lane == 0) r.terrain_levels[e] = lvl;
+    if (lane < 3) r.env_origins[e * 3 + lane] = r.terrain_origins[(lvl * r.n_terrain_types + r.terrain_types[e]) * 3 + lane];
+    __syncwarp();
+  }
+  // ---- _reset_dofs (LR:690-716)
+  if (parts & HL_RESET_DOFS) {
+    float ratio = 1.0f, vel = 0.0f;
+#pragma unroll
+    for (int d = 0; d < 12; ++d) {
+      const float ud = ru.get(d), uv = ru.get(12 + d);
+      if (lane == d) {
+        if (r.randomize_dof_pos) ratio = (r.dof_pos_ratio[1] - r.dof_pos_ratio[0]) * ud + r.dof_pos_ratio[0];
+        if (r.randomize_dof_vel) vel = uv * fabsf(r.dof_vel_range[1] - r.dof_vel_range[0]) + fminf(r.dof_vel_range[0], r.dof_vel_range[1]);
+      }
+    }
+    if (lane < 12) {
+      r.dof_state[e * 24 + 2 * lane] = c.default_dof_pos[lane] * ratio;
+      r.dof_state[e * 24 + 2 * lane + 1] = vel;
+    }
+  }
+  // ---- _reset_root_states (LR:718-820)
+  if (parts & HL_RESET_ROOT) {
+    float px = r.base_init_state[0] + r.env_origins[e * 3 + 0], py = r.base_init_state[1] + r.env_origins[e * 3 + 1],
+          pz = r.base_init_state[2] + r.env_origins[e * 3 + 2];
+    const float ux = ru.get(24), uy = ru.get(25), uz = ru.get(26);
+    if (r.custom_origins) {
+      if (r.has_pos_range) {
+        px += (r.pos_range[1] - r.pos_range[0]) * ux + r.pos_range[0];
+        py += (r.pos_range[3] - r.pos_range[2]) * uy + r.pos_range[2];
+        pz += (r.pos_range[5] - r.pos_range[4]) * uz + r.pos_range[4];
+      } else {
+        px += (1.0f - (-1.0f)) * ux + (-1.0f);
+        py += (1.0f - (-1.0f)) * uy + (-1.0f);
+      }
+    }
+    float q[4] = {r.base_init_state[3], r.base_init_state[4], r.base_init_state[5], r.base_init_state[6]};
+    const float ur = ru.get(27), up_ = ru.get(28), uyw = ru.get(29);
+    if (r.has_rot_range) {   // quat_from_euler_xyz(roll, pitch, yaw) (isaacgym.torch_utils)
+      const float roll = (r.rot_range[1] - r.rot_range[0]) * ur + r.rot_range[0], pitch = (r.rot_range[3] - r.rot_range[2]) * up_ + r.rot_range[2],
+                  yaw = (r.rot_range[5] - r.rot_range[4]) * uyw + r.rot_range[4];
+      const float cy = cosf(yaw * 0.5f), sy = sinf(yaw * 0.5f), cr = cosf(roll * 0.5f), sr = sinf(roll * 0.5f), cp = cosf(pitch * 0.5f),
+                  sp = sinf(pitch * 0.5f);
+      q[0] = cy * sr * cp - sy * cr * sp;
+      q[1] = cy * cr * sp + sy * sr * cp;
+      q[2] = sy * cr * cp - cy * sr * sp;
+      q[3] = cy * cr * cp + sy * sr * sp;
+    }
+    float vel6 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float u = ru.get(30 + k);
+      const float* lohi = r.vel_range_is_dict ? r.vel_range + 2 * k : r.vel_range;
+      if (lane == k) vel6 = (lohi[1] - lohi[0]) * u + lohi[0];
+    }
+    if (lane == 0) {
+      float* rs = r.root_states + e * 13;
+      rs[0] = px; rs[1] = py; rs[2] = pz;
+      rs[3] = q[0]; rs[4] = q[1]; rs[5] = q[2]; rs[6] = q[3];
+    }
+    if (lane < 6) r.root_states[e * 13 + 7 + lane] = vel6;
+  }
+  // ---- _resample_commands (LR:634-656)
+  if (parts & HL_RESET_COMMANDS) hl_resample_env(r, ru, e, gid, lane);
+  // ---- Kp / Kd / motor-strength factors (LR:336-341)
+  if (parts & HL_RESET_FACTORS) {
+    const float ukp = ru.get(40), ukd = ru.get(41), ums = ru.get(42);
+    if (lane == 0) {
+      if (r.randomize_kp && r.kp_factors) r.kp_factors[e] = (r.kp_range[1] - r.kp_range[0]) * ukp + r.kp_range[0];
+      if (r.randomize_kd && r.kd_factors) r.kd_factors[e] = (r.kd_range[1] - r.kd_range[0]) * ukd + r.kd_range[0];
+      if (r.randomize_motor_strength && r.motor_strength_factors)
+        r.motor_strength_factors[e] = (r.motor_strength_range[1] - r.motor_strength_range[0]) * ums + r.motor_strength_range[0];
+    }
+  }
+  __syncwarp();
+}
+
 template <unsigned STAGES, bool SPLIT = false>  // STAGES 0 = take the mask at run time; otherwise everything else is compiled out
 __global__ void __launch_bounds__(256, 3) hl_stage_kernel(HlCfg c, HlEnvBuffers b, unsigned stages_rt,
                                                        const long long* __restrict__ ids,
-                                                       const int* __restrict__ n_ids, long long n, int parts) {
+                                                       const int* __restrict__ n_ids, long long n, int parts, HlReset rs) {
   // parts > 1 (post-reset fix-up only): an env is spread over `parts` warps -- warp 0 ("lead") does the
   // buffer resets, slot 0 / privileged_obs[0:51] and the roll, warps 1.. the height iterations
   // it % (parts-1) == part-1 (scan + height part of privileged_obs): shorter dependent chains for the
@@ -410,6 +550,7 @@ __global__ void __launch_bounds__(256, 3) hl_stage_kernel(HlCfg c, HlEnvBuffers 
     const long long e = ids ? ids[it0] : it0;
     if (e < 0 || e >= n) continue;
     __syncwarp();   // the previous env's staged records are no longer read
+    if ((stages & HL_ST_RESET_DRAW) && lead) hl_reset_draw_env(c, b, rs, e, lane);   // writes the env's root / dof / command rows
     EnvView v;
     hl_stage_env(st, c, b, e, lane, (stages & HL_ST_RESET_ZERO) != 0, v);
     if ((stages & HL_ST_RESET_ZERO) && lead) {  // LR:323-329,350,361
@@ -603,8 +744,15 @@ __global__ void __launch_bounds__(256, 3) hl_stage_kernel(HlCfg c, HlEnvBuffers 
 }
 
 static int launch_stage(const HlCfg* cfg, const HlEnvBuffers* bufs, unsigned stages, const int64_t* ids,
-                        const int32_t* n_ids, int64_t n, void* stream) {
+                        const int32_t* n_ids, int64_t n, void* stream, const HlReset* reset = nullptr) {
   if (int r = check_cfg(cfg, bufs)) return r;
+  HlReset rs = {};
+  if (stages & HL_ST_RESET_DRAW) {
+    HL_CHECK_ARG(reset && reset->struct_bytes == (int)sizeof(HlReset), "HL_ST_RESET_DRAW needs a HlReset (size mismatch?)");
+    HL_CHECK_ARG(reset->root_states && reset->dof_state && reset->commands && reset->env_origins, "HlReset: null state tensor");
+    HL_CHECK_ARG(ids && n_ids, "HL_ST_RESET_DRAW runs on a reset id list");
+    rs = *reset;
+  }
   HL_CHECK_ARG((ids == nullptr) == (n_ids == nullptr), "env_ids and n_ids_dev go together");
   if (n <= 0) return HL_OK;
   long long blocks = (n * 32 + 255) / 256;
@@ -614,21 +762,24 @@ static int launch_stage(const HlCfg* cfg, const HlEnvBuffers* bufs, unsigned sta
   static const int fix_parts_env = [] { const char* e = getenv("HL_FIX_PARTS"); return e ? atoi(e) : 4; }();
   // small shards are latency-bound (a few hundred reset envs on 148 SMs): spread each env over several
   // warps; at 65,536 envs the extra staging costs more than the shorter chains save (measured)
-  const int fix_parts = (ids && cfg->measure_heights && cfg->mesh_type != 0 && fix_parts_env > 1 && n <= 16384) ? fix_parts_env : 1;
+  // (a split env would have its scan warps read the root record while the lead warp re-draws it: no split with RESET_DRAW)
+  const int fix_parts = (ids && cfg->measure_heights && cfg->mesh_type != 0 && fix_parts_env > 1 && n <= 16384 && !(stages & HL_ST_RESET_DRAW)) ? fix_parts_env : 1;
   constexpr unsigned FIX = HL_ST_HEIGHTS | HL_ST_OBS | HL_ST_OBS_NOSHIFT | HL_ST_OBS_CLIP | HL_ST_ROLL;
   const cudaStream_t st = (cudaStream_t)stream;
   if (stages == FIX)
   {
-    if (fix_parts > 1) hl_launch(hl_stage_kernel<FIX, true>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, fix_parts);
-    else hl_launch(hl_stage_kernel<FIX, false>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, 1);
+    if (fix_parts > 1) hl_launch(hl_stage_kernel<FIX, true>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, fix_parts, rs);
+    else hl_launch(hl_stage_kernel<FIX, false>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, 1, rs);
   }
   else if (stages == (FIX | HL_ST_RESET_ZERO))
   {
-    if (fix_parts > 1) hl_launch(hl_stage_kernel<FIX | HL_ST_RESET_ZERO, true>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, fix_parts);
-    else hl_launch(hl_stage_kernel<FIX | HL_ST_RESET_ZERO, false>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, 1);
+    if (fix_parts > 1) hl_launch(hl_stage_kernel<FIX | HL_ST_RESET_ZERO, true>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, fix_parts, rs);
+    else hl_launch(hl_stage_kernel<FIX | HL_ST_RESET_ZERO, false>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, 1, rs);
   }
+  else if (stages == (FIX | HL_ST_RESET_ZERO | HL_ST_RESET_DRAW))
+    hl_launch(hl_stage_kernel<FIX | HL_ST_RESET_ZERO | HL_ST_RESET_DRAW, false>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, 1, rs);
   else
-    hl_launch(hl_stage_kernel<0u, false>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, 1);
+    hl_launch(hl_stage_kernel<0u, false>, dim3((unsigned)blocks), dim3(256), stage_smem, st, *cfg, *bufs, stages, (const long long*)ids, n_ids, n, 1, rs);
   HL_CHECK_LAUNCH();
   return HL_OK;
 }
@@ -645,6 +796,77 @@ extern "C" int hl_post_reset_fixup(const HlCfg* cfg, const HlEnvBuffers* bufs, c
                       HL_ST_HEIGHTS | HL_ST_OBS | HL_ST_OBS_NOSHIFT | HL_ST_OBS_CLIP | HL_ST_ROLL |
                           (with_reset_zero ? HL_ST_RESET_ZERO : 0u),
                       env_ids, n_ids_dev, n, stream);
+}
+
+extern "C" int hl_sizeof_reset(void) { return (int)sizeof(HlReset); }
+
+extern "C" int hl_reset_idx(const HlCfg* cfg, const HlEnvBuffers* bufs, const HlReset* reset, const int64_t* env_ids,
+                            const int32_t* n_ids_dev, int64_t n, void* stream) {
+  return launch_stage(cfg, bufs, HL_ST_RESET_ZERO | HL_ST_RESET_DRAW, env_ids, n_ids_dev, n, stream, reset);
+}
+
+extern "C" int hl_reset_draw(const HlCfg* cfg, const HlEnvBuffers* bufs, const HlReset* reset, const int64_t* env_ids,
+                             const int32_t* n_ids_dev, int64_t n, void* stream) {
+  return launch_stage(cfg, bufs, HL_ST_RESET_DRAW, env_ids, n_ids_dev, n, stream, reset);
+}
+
+extern "C" int hl_reset_and_fixup(const HlCfg* cfg, const HlEnvBuffers* bufs, const HlReset* reset, const int64_t* env_ids,
+                                  const int32_t* n_ids_dev, int64_t n, void* stream) {
+  return launch_stage(cfg, bufs,
+                      HL_ST_HEIGHTS | HL_ST_OBS | HL_ST_OBS_NOSHIFT | HL_ST_OBS_CLIP | HL_ST_ROLL | HL_ST_RESET_ZERO | HL_ST_RESET_DRAW,
+                      env_ids, n_ids_dev, n, stream, reset);
+}
+
+// _resample_commands: one thread per candidate env.  The four uniforms are block 9 (columns 36-39) of the env's
+// reset-uniform vector, so this matches hl_reset_draw_env's command part for the same (seed, offset, env, stream).
+__global__ void __launch_bounds__(256) hl_resample_kernel(HlCfg c, HlEnvBuffers b, HlReset r, const long long* __restrict__ ids,
+                                                          const int* __restrict__ n_ids, long long interval, long long n) {
+  hl_pdl_enter();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long e;
+  if (ids) {
+    if (t >= (long long)*n_ids) return;
+    e = ids[t];
+    if (e < 0 || e >= n) return;
+  } else {
+    if (t >= n) return;
+    e = t;
+    if (interval <= 0 || (b.episode_length_buf[e] + 1) % interval != 0) return;   // LR:612 after LR:193's increment
+  }
+  const long long gid = e + c.env_id_offset;
+  float u[4];
+  if (r.uniforms) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = r.uniforms[e * HL_RESET_NU + 36 + k];
+  } else {
+    const uint4 q = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)gid, 9u, ids ? 3u : 2u);
+    u[0] = hl_u01(q.x); u[1] = hl_u01(q.y); u[2] = hl_u01(q.z); u[3] = hl_u01(q.w);
+  }
+  float c0 = (1.0f - (-1.0f)) * u[0] + (-1.0f);
+  float c1 = (r.cmd_lin_vel_y[1] - r.cmd_lin_vel_y[0]) * u[1] + r.cmd_lin_vel_y[0];
+  const float* lohi = r.heading_command ? r.cmd_heading : r.cmd_ang_vel_yaw;
+  const float c3 = (lohi[1] - lohi[0]) * u[2] + lohi[0];
+  if ((double)gid < (double)r.num_envs_global * (double)r.high_vel_frac) {
+    c0 = (r.cmd_lin_vel_x[1] - r.cmd_lin_vel_x[0]) * u[3] + r.cmd_lin_vel_x[0];
+    c1 *= fabsf(c0) < 1.0f ? 1.0f : 0.0f;
+  }
+  const float keep = sqrtf(c0 * c0 + c1 * c1) > 0.2f ? 1.0f : 0.0f;
+  r.commands[e * 4 + 0] = c0 * keep;
+  r.commands[e * 4 + 1] = c1 * keep;
+  r.commands[e * 4 + (r.heading_command ? 3 : 2)] = c3;
+}
+
+extern "C" int hl_resample_commands(const HlCfg* cfg, const HlEnvBuffers* bufs, const HlReset* reset, const int64_t* env_ids,
+                                    const int32_t* n_ids_dev, int64_t interval, int64_t n, void* stream) {
+  if (int r = check_cfg(cfg, bufs)) return r;
+  HL_CHECK_ARG(reset && reset->struct_bytes == (int)sizeof(HlReset) && reset->commands, "needs a HlReset with the commands tensor");
+  HL_CHECK_ARG((env_ids == nullptr) == (n_ids_dev == nullptr), "env_ids and n_ids_dev go together");
+  HL_CHECK_ARG(env_ids || bufs->episode_length_buf, "the pre-step form needs episode_length_buf");
+  if (n <= 0) return HL_OK;
+  hl_launch(hl_resample_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, *cfg, *bufs, *reset,
+            (const long long*)env_ids, n_ids_dev, (long long)interval, (long long)n);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
 }
 
 // one env's records for the terminal rows (root 13 | dof 24 | act 12), staged per warp
@@ -942,7 +1164,7 @@ __global__ void __launch_bounds__(256) hl_episode_means_kernel(float* __restrict
   if (tid == 0) {
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += part[w];
-    out[k] = cnt > 0 ? (float)(t / (double)cnt) : 0.0f;
+    if (cnt > 0) out[k] = (float)(t / (double)cnt);   // no reset: reset_idx returns early (LR:298-299), the logged value stays
   }
 }
 

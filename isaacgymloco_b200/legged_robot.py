@@ -18,13 +18,14 @@ Fused step (post_physics_step):
     hl_post_reset_fixup        re-scan + obs slot 0 + roll for the reset envs       LR:232-241,332-333
 """
 import ctypes
+import math
 import os
 from typing import Callable, Dict, Optional
 
 import torch
 
 from . import _lib as L
-from .config import HotPathCfg
+from .config import HlReset, HotPathCfg
 
 
 class FusedLeggedRobot:
@@ -147,7 +148,10 @@ class FusedLeggedRobot:
         self._bufs = None
         self._fused_event_hook = None      # bench.py: CUDA-event pair around the fused kernel
         self._rollout = None               # bind_rollout(): storage whose slots the env writes in place
+        self._philox_bias = 0
+        self._reset_sets_physx = False
         self._prepare_terrain()
+        self._init_reset_state()
 
     # ------------------------------------------------------------------ plumbing
     def _prepare_terrain(self):
@@ -208,7 +212,7 @@ class FusedLeggedRobot:
 
     def _buffers(self) -> L.HlEnvBuffers:
         if self._bufs is not None:
-            self._bufs.philox_offset = self.common_step_counter
+            self._bufs.philox_offset = self.common_step_counter + self._philox_bias
             return self._bufs
         b = L.HlEnvBuffers()
         b.struct_bytes = ctypes.sizeof(L.HlEnvBuffers)
@@ -233,7 +237,7 @@ class FusedLeggedRobot:
         b.obs_buf_in = b.obs_buf_out = p(self.obs_buf)
         b.privileged_obs_buf = p(self.privileged_obs_buf)
         b.noise_u45, b.noise_u187 = p(self._noise.get("obs45")), p(self._noise.get("obs187"))
-        b.philox_seed, b.philox_offset = self._philox_seed, self.common_step_counter
+        b.philox_seed, b.philox_offset = self._philox_seed, self.common_step_counter + self._philox_bias
         b.height_idx_out = None
         b.base_height_out = p(self._base_heights)
         if self.single_launch:
@@ -359,61 +363,318 @@ class FusedLeggedRobot:
         L.check(L.lib.hl_post_reset_fixup(ctypes.byref(self._c), ctypes.byref(self._buffers()), L.ptr(self._reset_ids),
                                           L.ptr(self._n_reset), int(with_reset_zero), self.num_envs, L.stream()))
 
+    # ------------------------------------------------------------------ reset state (LR:288-361) in the kernel chain
+    def _init_reset_state(self):
+        """Buffers reset_idx needs on top of the hot-path ones (LR:1221-1250,1013-1023); idempotent."""
+        dev, n, R = self.device, self.num_envs, self.cfg_hot.reset
+        z = lambda *shape, **kw: torch.zeros(*shape, device=dev, **kw)
+        if not isinstance(getattr(self, "env_origins", None), torch.Tensor):
+            self.env_origins = z(n, 3)
+        if not hasattr(self, "custom_origins"):
+            self.custom_origins = not self.cfg_hot.is_plane            # LR:1226
+        if not hasattr(self, "terrain_origins"):
+            self.terrain_origins, self.terrain_types = None, None
+        if not hasattr(self, "max_terrain_level"):
+            self.max_terrain_level = self.cfg_hot.num_rows               # LR:1235
+        if not isinstance(getattr(self, "motor_strength_factors", None), torch.Tensor):
+            self.motor_strength_factors = torch.ones(n, 1, device=dev)  # LR:1013
+        if not isinstance(getattr(self, "base_init_state", None), torch.Tensor):
+            self.base_init_state = torch.tensor(R.base_init_state, device=dev)
+        self._base_init_host = [float(x) for x in self.base_init_state.tolist()]   # host copy: no sync per step
+        if not hasattr(self, "command_ranges"):
+            self.command_ranges = dict(lin_vel_x=list(R.lin_vel_x), lin_vel_y=list(R.lin_vel_y),
+                                       ang_vel_yaw=list(R.ang_vel_yaw), heading=list(R.heading))
+        if not hasattr(self, "init_done"):
+            self.init_done = True
+        self._reset_uniforms = None           # parity mode: (N, RESET_NU) pre-drawn U[0,1)
+        self._episode_means = z(max(self._episode_sums_buf.shape[0], 1))
+        self.push_interval = int(math.ceil(self.cfg_hot.push_interval_s / self.dt))     # LR:1263
+        self.resample_interval = int(self.cfg_hot.resampling_time / self.dt)            # LR:612
+        self.max_episode_length_s = self.cfg_hot.episode_length_s
+
+    def set_reset_uniforms(self, u):
+        """Parity mode for the in-kernel reset_idx / _resample_commands: row e of `u` (N, 44) holds the
+        U[0,1) draws env e consumes (column map: include/himloco_b200.h).  None => in-kernel Philox."""
+        self._reset_uniforms = None if u is None else u.to(self.device, torch.float32).contiguous()
+
+    def _reset_struct(self, parts: int = 0) -> HlReset:
+        R, r = self.cfg_hot.reset, HlReset()
+        r.struct_bytes = ctypes.sizeof(HlReset)
+        r.custom_origins = int(bool(self.custom_origins))
+        pr, rr, vr = R.base_init_pos_range, R.base_init_rot_range, R.base_init_vel_range
+        r.has_pos_range = int(pr is not None)
+        if pr is not None:
+            r.pos_range[:] = [*pr["x"], *pr["y"], *pr["z"]]
+        r.has_rot_range = int(rr is not None)
+        if rr is not None:
+            r.rot_range[:] = [*rr["roll"], *rr["pitch"], *rr.get("yaw", [-math.pi, math.pi])]
+        if isinstance(vr, dict):
+            r.vel_range_is_dict = 1
+            r.vel_range[:] = [*vr["x"], *vr["y"], *vr["z"], *vr["roll"], *vr["pitch"], *vr["yaw"]]
+        elif isinstance(vr, (tuple, list)):
+            r.vel_range[0], r.vel_range[1] = vr[0], vr[1]
+        else:
+            raise NameError(f"Unknown base_vel_range type: {type(vr)}")           # LR:818
+        r.randomize_dof_pos = int(R.dof_init_pos_ratio_range is not None)
+        if R.dof_init_pos_ratio_range is not None:
+            r.dof_pos_ratio[:] = R.dof_init_pos_ratio_range
+        r.randomize_dof_vel = int(R.randomize_dof_vel)
+        r.dof_vel_range[:] = R.dof_init_vel_range
+        r.randomize_kp, r.randomize_kd, r.randomize_motor_strength = int(R.randomize_kp), int(R.randomize_kd), int(R.randomize_motor_strength)
+        r.kp_range[:], r.kd_range[:], r.motor_strength_range[:] = R.kp_range, R.kd_range, R.motor_strength_range
+        r.heading_command = int(self.cfg_hot.heading_command)
+        cr = self.command_ranges
+        r.cmd_lin_vel_x[:], r.cmd_lin_vel_y[:] = cr["lin_vel_x"], cr["lin_vel_y"]
+        r.cmd_ang_vel_yaw[:], r.cmd_heading[:] = cr["ang_vel_yaw"], cr["heading"]
+        r.high_vel_frac = 0.2
+        r.num_envs_global = self.cfg_hot.num_envs
+        has_cur = R.terrain_curriculum and self.init_done and self.terrain_origins is not None and self.terrain_types is not None
+        r.terrain_curriculum = int(bool(has_cur))
+        r.max_terrain_level = int(self.max_terrain_level)
+        r.n_terrain_types = int(self.terrain_origins.shape[1]) if self.terrain_origins is not None else 0
+        r.env_length = float(self.cfg_hot.terrain_length)
+        r.max_episode_length_s = float(self.max_episode_length_s)
+        r.base_init_state[:] = self._base_init_host
+        r.parts = parts
+        p = L.ptr
+        r.root_states, r.dof_state, r.commands = p(self.root_states), p(self.dof_state), p(self.commands)
+        r.env_origins, r.terrain_origins = p(self.env_origins), p(self.terrain_origins)
+        r.terrain_levels, r.terrain_types = p(self.terrain_levels), p(self.terrain_types)
+        r.kp_factors, r.kd_factors = p(self.Kp_factors), p(self.Kd_factors)
+        r.motor_strength_factors = p(self.motor_strength_factors)
+        r.uniforms = p(self._reset_uniforms)
+        return r
+
+    def _ids_arg(self, env_ids):
+        env_ids = env_ids.to(self.device, torch.long).contiguous()
+        return env_ids, torch.tensor([env_ids.numel()], dtype=torch.int32, device=self.device)
+
+    def _reset_part(self, env_ids, parts):
+        if len(env_ids) == 0:
+            return
+        ids, cnt = self._ids_arg(env_ids)
+        r = self._reset_struct(parts)
+        if parts == L.RESET_COMMANDS:
+            L.check(L.lib.hl_resample_commands(ctypes.byref(self._c), ctypes.byref(self._buffers()), ctypes.byref(r), L.ptr(ids),
+                                               L.ptr(cnt), 0, self.num_envs, L.stream()))
+            return
+        # the individual hooks: only that part, no buffer zeroing
+        L.check(L.lib.hl_reset_draw(ctypes.byref(self._c), ctypes.byref(self._buffers()), ctypes.byref(r), L.ptr(ids), L.ptr(cnt),
+                                   self.num_envs, L.stream()))
+
+    # the reference's hooks: in-kernel by default (Philox); subclass / mix in torch versions to override
+    def _reset_dofs(self, env_ids):
+        """LR:690-716 (the PhysX setter the reference calls at the end stays with the caller)."""
+        self._reset_part(env_ids, L.RESET_DOFS)
+        gym = getattr(self, "gym", None)
+        if gym is not None and len(env_ids):
+            gym.set_dof_state_tensor_indexed(self.sim, self.dof_state, env_ids.to(torch.int32), len(env_ids))
+
+    def _reset_root_states(self, env_ids):
+        """LR:718-820."""
+        self._reset_part(env_ids, L.RESET_ROOT)
+        gym = getattr(self, "gym", None)
+        if gym is not None and len(env_ids):
+            gym.set_actor_root_state_tensor_indexed(self.sim, self.root_states, env_ids.to(torch.int32), len(env_ids))
+
+    def _resample_commands(self, env_ids):
+        """LR:634-656."""
+        self._reset_part(env_ids, L.RESET_COMMANDS)
+
+    def _update_terrain_curriculum(self, env_ids):
+        """LR:845-866."""
+        if self.init_done and self.terrain_origins is not None:
+            self._reset_part(env_ids, L.RESET_CURRICULUM)
+
+    def reset_idx_device(self, env_ids, n_ids_dev=None, fixup=False):
+        """reset_idx's kernel form on a device id list (count on the device): curriculum, state re-draws, buffer
+        zeroing [+ the post-reset fix-up].  No host sync."""
+        if n_ids_dev is None:
+            env_ids, n_ids_dev = self._ids_arg(env_ids)
+        r = self._reset_struct()
+        fn = L.lib.hl_reset_and_fixup if fixup else L.lib.hl_reset_idx
+        L.check(fn(ctypes.byref(self._c), ctypes.byref(self._buffers()), ctypes.byref(r), L.ptr(env_ids), L.ptr(n_ids_dev),
+                   self.num_envs, L.stream()))
+
+    def _kernel_reset_ok(self) -> bool:
+        """True when none of the three state hooks is overridden: reset_idx then runs in the kernel chain."""
+        base = FusedLeggedRobot
+        t = type(self)
+        return (t._reset_dofs is base._reset_dofs and t._reset_root_states is base._reset_root_states
+                and t._resample_commands is base._resample_commands and t.reset_idx is base.reset_idx)
+
+    def _push_robots(self):
+        """LR:822-828 (torch RNG; PhysX-facing)."""
+        mv = self.cfg_hot.reset.max_push_vel_xy
+        self.root_states[:, 7:9] = (2 * mv) * torch.rand(self.num_envs, 2, device=self.device) - mv
+        gym = getattr(self, "gym", None)
+        if gym is not None:
+            gym.set_actor_root_state_tensor(self.sim, self.root_states)
+
+    def _disturbance_robots(self):
+        """LR:838-844 (torch RNG; PhysX-facing)."""
+        lo, hi = self.cfg_hot.reset.disturbance_range
+        self.disturbance[:, 0, :] = (hi - lo) * torch.rand(self.num_envs, 3, device=self.device) + lo
+        gym = getattr(self, "gym", None)
+        if gym is not None:
+            gym.apply_rigid_body_force_tensors(self.sim, forceTensor=self.disturbance, space="LOCAL_SPACE")
+
+    def update_command_curriculum(self, env_ids):
+        """LR:868-880 (host state: the shared command ranges)."""
+        import numpy as np
+        R = self.cfg_hot.reset
+        if "tracking_lin_vel" not in self.episode_sums or len(env_ids) == 0:
+            return
+        mean = torch.mean(self.episode_sums["tracking_lin_vel"][env_ids]) / self.max_episode_length
+        if float(mean) > 0.8 * self.reward_scales["tracking_lin_vel"]:
+            cr = self.command_ranges
+            cr["lin_vel_x"][0] = float(np.clip(cr["lin_vel_x"][0] - 0.1, -getattr(R, "max_backward_curriculum", 1.0), 0.))
+            cr["lin_vel_x"][1] = float(np.clip(cr["lin_vel_x"][1] + 0.1, 0., getattr(R, "max_forward_curriculum", 1.5)))
+            cr["lin_vel_y"][0] = float(np.clip(cr["lin_vel_y"][0] - 0.1, -getattr(R, "max_lat_curriculum", 1.0), 0.))
+            cr["lin_vel_y"][1] = float(np.clip(cr["lin_vel_y"][1] + 0.1, 0., getattr(R, "max_lat_curriculum", 1.0)))
+
+    def _pre_step_callbacks(self):
+        """The RNG-driven part of _post_physics_step_callback that precedes the fused step (LR:612-613,631-632):
+        commands of the envs whose incremented episode length hits the resampling interval (in-kernel, Philox
+        stream 2 or the parity uniforms), then the interval disturbance."""
+        R = self.cfg_hot.reset
+        if self.resample_interval > 0 and type(self)._resample_commands is FusedLeggedRobot._resample_commands:
+            r = self._reset_struct(L.RESET_COMMANDS)
+            L.check(L.lib.hl_resample_commands(ctypes.byref(self._c), ctypes.byref(self._buffers()), ctypes.byref(r), None, None,
+                                               self.resample_interval, self.num_envs, L.stream()))
+        elif self.resample_interval > 0:
+            ids = ((self.episode_length_buf + 1) % self.resample_interval == 0).nonzero(as_tuple=False).flatten()
+            self._resample_commands(ids)
+        if R.disturbance and self.common_step_counter % self.cfg_hot.disturbance_interval == 0:
+            self._disturbance_robots()
+
+    def _log_episode(self, env_ids=None):
+        """extras of reset_idx (LR:344-359); the masked means come from one launch over the device id list."""
+        L.check(L.lib.hl_episode_means(L.ptr(self._episode_sums_buf), L.ptr(self.episode_length_buf), L.ptr(self._reset_ids),
+                                       L.ptr(self._n_reset), self._episode_sums_buf.shape[0], self.num_envs, float(self.dt), 1,
+                                       L.ptr(self._episode_means), L.stream()))
+        ep = self.extras.setdefault("episode", {})
+        for k, key in enumerate(self.episode_sums.keys()):
+            ep["rew_" + key] = self._episode_means[k]
+        if self.cfg_hot.reset.terrain_curriculum and self.terrain_origins is not None:
+            ep["terrain_level"] = torch.mean(self.terrain_levels.float())
+        if self.cfg_hot.reset.commands_curriculum:
+            ep["max_command_x"] = self.command_ranges["lin_vel_x"][1]
+        self.extras["time_outs"] = self.time_out_buf
+
+    def post_physics_step_device(self):
+        """LR:178-247 as ONE chain of launches without a host sync (CUDA-graph capturable when no torch hook is
+        overridden): returns the capacity-N id / terminal-row buffers and the device count.  post_physics_step()
+        is this plus the one `.item()` the reference's return signature needs, issued after everything is queued."""
+        R = self.cfg_hot.reset
+        gym = getattr(self, "gym", None)
+        if gym is not None:                                   # LR:187-190
+            gym.refresh_actor_root_state_tensor(self.sim)
+            gym.refresh_net_contact_force_tensor(self.sim)
+            gym.refresh_force_sensor_tensor(self.sim)
+            gym.refresh_rigid_body_state_tensor(self.sim)
+        self.common_step_counter += 1                         # LR:194 (episode_length_buf += 1 happens in the kernel)
+        self._philox_bias = -1                                # noise streams stay keyed by the step index 0, 1, 2, ...
+        try:
+            push_now = R.push_robots and self.push_interval > 0 and self.common_step_counter % self.push_interval == 0
+            self._pre_step_callbacks()
+            if push_now:
+                # LR:627-628: the push changes root_states[:, 7:9] AFTER base_lin_vel was taken and BEFORE rewards /
+                # observations: the staged path splits the step around it (1 step in push_interval)
+                self._stages(L.ST_COUNTERS | L.ST_FRAME | L.ST_CONTACTS)
+                self._push_robots()
+                self._stages(L.ST_HEADING | L.ST_HEIGHTS | L.ST_TERMINATION | L.ST_REWARD)
+                bufs = self._buffers()
+                L.check(L.lib.hl_select_and_terminal(ctypes.byref(self._c), ctypes.byref(bufs), L.ptr(self._noise.get("term45")),
+                                                     L.ptr(self._noise.get("term187")), L.ptr(self._reset_ids), L.ptr(self._n_reset),
+                                                     L.ptr(self._term_priv), L.ptr(self._term_amp), L.ptr(self._selterm_ws),
+                                                     self.num_envs, L.stream()))
+            else:
+                self.fused_pre_reset()
+            if self._kernel_reset_ok():
+                if R.commands_curriculum and self.common_step_counter % self.max_episode_length == 0:   # LR:306-307 (1 step in 1000)
+                    self.update_command_curriculum(self._reset_ids[:int(self._n_reset.item())])
+                self._log_episode()
+                r = self._reset_struct()
+                c, b = ctypes.byref(self._c), ctypes.byref(self._buffers())
+                if push_now:
+                    L.check(L.lib.hl_reset_idx(c, b, ctypes.byref(r), L.ptr(self._reset_ids), L.ptr(self._n_reset), self.num_envs, L.stream()))
+                    self._stages(L.ST_HEIGHTS, self._reset_ids, self._n_reset)
+                    self._stages(L.ST_OBS | L.ST_OBS_CLIP | L.ST_ROLL)
+                else:
+                    L.check(L.lib.hl_reset_and_fixup(c, b, ctypes.byref(r), L.ptr(self._reset_ids), L.ptr(self._n_reset), self.num_envs,
+                                                     L.stream()))
+                self._reset_sets_physx = True
+            else:
+                n_reset = int(self._n_reset.item())          # torch hooks need the ids on the host side (LR:225,298)
+                self.reset_idx(self._reset_ids[:n_reset])
+                if push_now:
+                    self._stages(L.ST_HEIGHTS, self._reset_ids, self._n_reset)
+                    self._stages(L.ST_OBS | L.ST_OBS_CLIP | L.ST_ROLL)
+                else:
+                    self.fused_post_reset()
+        finally:
+            self._philox_bias = 0
+        return self._reset_ids, self._n_reset, self._term_priv, self._term_amp
+
     def post_physics_step(self):
         """LR:178-247 -> (env_ids, termination_privileged_obs, terminal_amp_states)."""
-        self._pre_step_callbacks()
-        self.fused_pre_reset()
-        n_reset = int(self._n_reset.item())          # the reference syncs here too (LR:225,298)
-        env_ids = self._reset_ids[:n_reset]
-        term_priv, term_amp = self._term_priv[:n_reset], self._term_amp[:n_reset]
-        self.reset_idx(env_ids)
-        self.fused_post_reset()
-        self.common_step_counter += 1
-        return env_ids, term_priv, term_amp
+        ids, n_dev, term_priv, term_amp = self.post_physics_step_device()
+        n_reset = int(n_dev.item())                          # after the whole chain is queued: the GPU never waits for it
+        env_ids = ids[:n_reset]
+        gym = getattr(self, "gym", None)
+        if gym is not None and n_reset and getattr(self, "_reset_sets_physx", False):
+            ids32 = env_ids.to(torch.int32)                   # LR:713-716,817-820: hand the re-drawn rows to PhysX
+            gym.set_dof_state_tensor_indexed(self.sim, self.dof_state, ids32, n_reset)
+            gym.set_actor_root_state_tensor_indexed(self.sim, self.root_states, ids32, n_reset)
+        return env_ids, term_priv[:n_reset], term_amp[:n_reset]
 
     def step(self, actions):
-        """LR:122-176 (7-tuple; the AMP runner reads terminal_amp_states off `extras`)."""
+        """LR:122-176.  7-tuple, or the 8-tuple with terminal_amp_states when cfg.using_amp (LR:173-176)."""
         clip = self.cfg_hot.clip_actions
         torch.clamp(actions.to(self.device), -clip, clip, out=self.actions)
         self._delay_actions()
+        gym = getattr(self, "gym", None)
+        if gym is not None:
+            self.render() if hasattr(self, "render") else None
         for k in range(self.cfg_hot.decimation):
             self._compute_torques_into(self.delayed_actions[:, k], self.torques)
+            if gym is not None:                               # LR:148-152
+                gym.set_dof_actuation_force_tensor(self.sim, self.torques)
+                gym.simulate(self.sim)
+                gym.fetch_results(self.sim, True)
+                gym.refresh_dof_state_tensor(self.sim)
             if self.physics_step_fn is not None:
                 self.physics_step_fn(self, k)
         env_ids, term_priv, term_amp = self.post_physics_step()
         self.extras["terminal_amp_states"] = term_amp
-        return (self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras, env_ids, term_priv)
+        out = (self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras, env_ids, term_priv)
+        return out + (term_amp,) if self.cfg_hot.using_amp else out
 
-    # ------------------------------------------------------------------ torch-side hooks (RNG / PhysX; out of scope)
+    # ------------------------------------------------------------------ torch-side hooks (RNG / PhysX)
     def _delay_actions(self):
-        """LR:133-138 (torch RNG draw of the per-env action delay)."""
+        """LR:133-138: per-env random action delay, only when cfg.domain_rand.delay."""
         dec = self.cfg_hot.decimation
+        if not self.cfg_hot.reset.delay:
+            self.delayed_actions.copy_(self.actions.unsqueeze(1).expand(-1, dec, -1))
+            return
         delay = torch.randint(0, dec, (self.num_envs, 1), device=self.device)
         steps = torch.arange(dec, device=self.device).view(1, dec, 1)
         mask = (steps >= delay.view(-1, 1, 1)).to(self.actions.dtype)
         torch.add(self.last_actions.unsqueeze(1), (self.actions - self.last_actions).unsqueeze(1) * mask,
                   out=self.delayed_actions)
 
-    def _pre_step_callbacks(self):
-        """The RNG-driven part of _post_physics_step_callback (LR:612-613): resample commands of
-        envs whose *incremented* episode length hits the interval.  Hook; default = keep."""
-        return None
-
-    def _reset_dofs(self, env_ids):
-        return None
-
-    def _reset_root_states(self, env_ids):
-        return None
-
-    def _resample_commands(self, env_ids):
-        return None
-
     def reset_idx(self, env_ids):
-        """The deterministic bookkeeping of LR:288-361; state re-draws go through the three hooks
-        above.  The full-N height re-scan of LR:332-333 is replaced by the targeted re-scan in
-        hl_post_reset_fixup (identical result: non-reset envs did not move)."""
+        """LR:288-361 through the hooks (used when a hook is overridden with torch code, or when called directly);
+        post_physics_step runs the same work as one launch when no hook is overridden.  The full-N height re-scan
+        of LR:332-333 is replaced by the targeted re-scan of the fix-up (non-reset envs did not move)."""
         if len(env_ids) == 0:
             return
+        R = self.cfg_hot.reset
+        if R.terrain_curriculum:
+            self._update_terrain_curriculum(env_ids)
+        if R.commands_curriculum and (self.common_step_counter % self.max_episode_length == 0):
+            self.update_command_curriculum(env_ids)
         self._reset_dofs(env_ids)
         self._reset_root_states(env_ids)
         self._resample_commands(env_ids)
@@ -424,12 +685,13 @@ class FusedLeggedRobot:
         self.last_torques[env_ids] = 0.0
         self.feet_air_time[env_ids] = 0.0
         self.reset_buf[env_ids] = True
+        if type(self)._reset_dofs is FusedLeggedRobot._reset_dofs:   # LR:336-341 (kernel form: same uniform columns)
+            self._reset_part(env_ids, L.RESET_FACTORS)
         self.extras["episode"] = {}
         if self.episode_sums:   # LR:346-350 as one launch (means of every row over the reset ids, rows zeroed)
+            ids, cnt = self._ids_arg(env_ids)
             rows = self._episode_sums_buf.shape[0]
             means = torch.empty(rows, device=self.device)
-            ids = env_ids.to(self.device, torch.int64).contiguous()
-            cnt = torch.full((1,), ids.numel(), dtype=torch.int32, device=self.device)
             L.check(L.lib.hl_episode_means(L.ptr(self._episode_sums_buf), L.ptr(self.episode_length_buf), L.ptr(ids),
                                            L.ptr(cnt), rows, self.num_envs, float(self.dt), 1, L.ptr(means), L.stream()))
             for k, key in enumerate(self.episode_sums.keys()):

@@ -344,6 +344,94 @@ def mint_amp():
     np.savez_compressed(os.path.join(GOLDEN_DIR, "amp.npz"), **out)
     print(f"[golden] amp: clips={nclips} frames={sum(loader.trajectories_full[i].shape[0] for i in range(nclips))} blends={len(idx)}")
 
+# --------------------------------------------------------------------------- f2: reset_idx with its draws
+RESET_CASES = [dict(name="flat", task="flat", n=256, seed=51), dict(name="stairs", task="stairs", n=192, seed=52)]
+
+
+def reset_inputs(case):
+    """Seeded inputs of a reset golden: state, uniforms (N, 44), terrain-curriculum tables, the reset id list."""
+    cfg = C.aliengo(case["task"], num_envs=case["n"])
+    n = case["n"]
+    hf = S.make_terrain(cfg, seed=case["seed"])
+    state = S.make_state(cfg, n, hf, seed=case["seed"])
+    g = torch.Generator().manual_seed(case["seed"] + 7000)
+    u = torch.rand(n, C.RESET_NU, generator=g)
+    origins = torch.zeros(cfg.num_rows, cfg.num_cols, 3)
+    origins[..., 0] = (torch.arange(cfg.num_rows).float()[:, None] + 0.5) * cfg.terrain_length
+    origins[..., 1] = (torch.arange(cfg.num_cols).float()[None, :] + 0.5) * cfg.terrain_width
+    origins[..., 2] = 0.1 * torch.rand(cfg.num_rows, cfg.num_cols, generator=g)
+    types_ = torch.div(torch.arange(n), (n / cfg.num_cols), rounding_mode="floor").to(torch.long)      # LR:1234
+    levels = state["terrain_levels"].clone()
+    levels[: n // 8] = cfg.num_rows - 1                    # some at the top level: move_up sends them to a random one
+    env_origins = origins[levels, types_].clone()
+    # half of the envs walked far (move up), a quarter barely moved (move down)
+    state["root_states"][: n // 2, 0:2] = env_origins[: n // 2, 0:2] + cfg.terrain_length
+    state["root_states"][n // 2: 3 * n // 4, 0:2] = env_origins[n // 2: 3 * n // 4, 0:2] + 0.01
+    state["terrain_levels"] = levels
+    ids = (torch.rand(n, generator=g) < 0.4).nonzero(as_tuple=False).flatten()
+    return cfg, hf, state, u, dict(origins=origins, types=types_, env_origins=env_origins), ids
+
+
+def mint_reset():
+    H.install_stubs()
+    import legged_gym.envs.base.legged_robot as LRM
+    for case in RESET_CASES:
+        cfg, hf, state, u, ter, ids = reset_inputs(case)
+        n = case["n"]
+        env = H.build_reference_env(case["task"], state, hf, sum_names=cfg.episode_sum_names(), hot_cfg=cfg)
+        env.custom_origins = True
+        env.env_origins = ter["env_origins"].clone()
+        env.terrain_origins, env.terrain_types = ter["origins"].clone(), ter["types"].clone()
+        env.max_terrain_level = cfg.num_rows
+        rc = env.cfg
+        base = rc.init_state.pos + rc.init_state.rot + rc.init_state.lin_vel + rc.init_state.ang_vel
+        env.base_init_state = torch.tensor(base, dtype=torch.float)
+        env.refresh_actor_rigid_shape_props = types.MethodType(lambda self, *a, **k: None, env)
+        env.update_command_curriculum = types.MethodType(lambda self, *a, **k: None, env)
+        assert rc.terrain.curriculum and env.init_done
+        # the uniform columns in the reference's call order (include/himloco_b200.h: HL_RESET_NU)
+        plan = []
+        plan.append(("rand12", 0))                        # _reset_dofs: torch_rand_float(..., (len, 12))
+        for k in (24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38):
+            plan.append(("col", k))
+        plan.append(("high", 39))                         # _resample_commands: the high-speed prefix of env_ids
+        for k in (40, 41, 42):
+            plan.append(("col", k))
+        cursor = {"i": 0}
+
+        def fake_rand_float(lower, upper, shape, device):
+            kind, k = plan[cursor["i"]]
+            cursor["i"] += 1
+            if kind == "rand12":
+                assert tuple(shape) == (len(ids), 12)
+                uu = u[ids, 0:12]
+            elif kind == "high":
+                uu = u[ids[: shape[0]], 39:40]
+            else:
+                assert tuple(shape) == (len(ids), 1), (shape, k)
+                uu = u[ids, k:k + 1]
+            return (upper - lower) * uu + lower
+
+        real_rf, real_rl, real_ri = LRM.torch_rand_float, torch.rand_like, torch.randint_like
+        LRM.torch_rand_float = fake_rand_float
+        torch.rand_like = lambda t, *a, **k: u[ids, 12:24].clone()
+        torch.randint_like = lambda t, hi, *a, **k: (u[ids, 43] * hi).long().clamp(max=hi - 1)
+        try:
+            env.reset_idx(ids)
+        finally:
+            LRM.torch_rand_float, torch.rand_like, torch.randint_like = real_rf, real_rl, real_ri
+        assert cursor["i"] == len(plan), (cursor["i"], len(plan))
+        out = {"input_checksum": input_checksum(state), "ids": ids.numpy(), "u_checksum": np.float64(u.double().sum())}
+        for k in ("root_states", "dof_state", "commands", "Kp_factors", "Kd_factors", "motor_strength_factors", "terrain_levels",
+                  "env_origins", "last_actions", "last_last_actions", "last_dof_pos", "last_dof_vel", "last_torques",
+                  "feet_air_time", "episode_length_buf", "reset_buf", "measured_heights"):
+            out[k] = getattr(env, k).numpy().copy()
+        out["episode_sums"] = np.stack([env.episode_sums[k].numpy() for k in cfg.episode_sum_names()])
+        out["extras_names"] = np.array(sorted(k for k in env.extras["episode"] if k.startswith("rew_")))
+        out["extras_vals"] = np.array([float(env.extras["episode"][k]) for k in out["extras_names"]], dtype=np.float32)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"reset_{case['name']}.npz"), **out)
+        print(f"[golden] reset_{case['name']}: n={n} resets={len(ids)} levels moved={(out['terrain_levels'] != state['terrain_levels'].numpy()).sum()}")
+
 
 def main():
     assert H.reference_available(), "run in the build container (needs /root/reference)"
@@ -356,6 +444,7 @@ def main():
     mint_minibatch()
     mint_replay()
     mint_amp()
+    mint_reset()
 
 
 if __name__ == "__main__":

@@ -111,6 +111,14 @@ class OracleEnv:
         self.measured_heights = self._get_heights()
         self.common_step_counter = 0
         self.last_height_indices = None
+        rs = getattr(cfg, "reset", None)
+        if rs is not None:
+            self.command_ranges = dict(lin_vel_x=list(rs.lin_vel_x), lin_vel_y=list(rs.lin_vel_y),
+                                       ang_vel_yaw=list(rs.ang_vel_yaw), heading=list(rs.heading))
+        if not hasattr(self, "env_origins"):
+            self.env_origins = torch.zeros(n, 3, device=dev)
+        if not hasattr(self, "motor_strength_factors"):
+            self.motor_strength_factors = torch.ones(n, 1, device=dev)
 
     def _grid(self, xs, ys):
         """LR:1286-1316: x-major meshgrid of body-frame sample points, z = 0."""
@@ -547,6 +555,91 @@ class OracleEnv:
             self.apply_reset(env_ids, reset_targets)
         self.post_reset(noise)
         return env_ids, term_obs, term_amp
+
+    # ------------------------------------------------------------------ f2: reset_idx with its draws
+    # Every `torch_rand_float(lo, hi, ...)` of the reference becomes lo + (hi - lo) * u[:, k] with the column map of
+    # include/himloco_b200.h (HL_RESET_NU): the same uniforms the kernel consumes in parity mode.
+    def resample_commands(self, env_ids, u, rs):
+        """LR:634-656.  `rs` = cfg.reset (+ the live command ranges in rs_ranges)."""
+        if len(env_ids) == 0:
+            return
+        cr = self.command_ranges
+        U = u[env_ids]
+        rng = lambda k, lohi: (lohi[1] - lohi[0]) * U[:, k] + lohi[0]
+        self.commands[env_ids, 0] = rng(36, (-1.0, 1.0))
+        self.commands[env_ids, 1] = rng(37, cr["lin_vel_y"])
+        if self.cfg.heading_command:
+            self.commands[env_ids, 3] = rng(38, cr["heading"])
+        else:
+            self.commands[env_ids, 2] = rng(38, cr["ang_vel_yaw"])
+        gid = env_ids + self.cfg.env_id_offset
+        high = gid < (self.cfg.num_envs * 0.2)
+        hi_ids = env_ids[high.nonzero(as_tuple=True)]
+        self.commands[hi_ids, 0] = ((cr["lin_vel_x"][1] - cr["lin_vel_x"][0]) * u[hi_ids, 39] + cr["lin_vel_x"][0])
+        self.commands[hi_ids, 1:2] *= (torch.norm(self.commands[hi_ids, 0:1], dim=1) < 1.0).unsqueeze(1)
+        self.commands[env_ids, :2] *= (torch.norm(self.commands[env_ids, :2], dim=1) > 0.2).unsqueeze(1)
+
+    def reset_idx_draw(self, env_ids, u, custom_origins=True, terrain=None):
+        """LR:288-341: terrain curriculum, _reset_dofs, _reset_root_states, _resample_commands, gain factors.
+        `terrain` = dict(origins (L,T,3), types (N,), max_level, env_length, max_episode_length_s) or None."""
+        if len(env_ids) == 0:
+            return
+        rs = self.cfg.reset
+        n = self.num_envs
+        U = u[env_ids]
+        rng = lambda k, lohi: (lohi[1] - lohi[0]) * U[:, k] + lohi[0]
+        if terrain is not None and rs.terrain_curriculum:                     # LR:845-866
+            dist = torch.norm(self.root_states[env_ids, :2] - self.env_origins[env_ids, :2], dim=1)
+            up = dist > terrain["env_length"] / 2
+            down = (dist < torch.norm(self.commands[env_ids, :2], dim=1) * terrain["max_episode_length_s"] * 0.5) * ~up
+            lv = self.terrain_levels[env_ids] + 1 * up - 1 * down
+            rand_lv = (U[:, 43] * terrain["max_level"]).long().clamp(max=terrain["max_level"] - 1)
+            lv = torch.where(lv >= terrain["max_level"], rand_lv, torch.clip(lv, 0))
+            self.terrain_levels[env_ids] = lv
+            self.env_origins[env_ids] = terrain["origins"][lv, terrain["types"][env_ids]]
+        # _reset_dofs (LR:690-716)
+        dp = self.dof_state.view(n, 12, 2)
+        if rs.dof_init_pos_ratio_range is not None:
+            dp[env_ids, :, 0] = self.default_dof_pos * ((rs.dof_init_pos_ratio_range[1] - rs.dof_init_pos_ratio_range[0]) * U[:, 0:12]
+                                                        + rs.dof_init_pos_ratio_range[0])
+        else:
+            dp[env_ids, :, 0] = self.default_dof_pos.expand(len(env_ids), 12)
+        if rs.randomize_dof_vel:
+            r = rs.dof_init_vel_range
+            dp[env_ids, :, 1] = U[:, 12:24] * abs(r[1] - r[0]) + min(r)
+        else:
+            dp[env_ids, :, 1] = 0.0
+        # _reset_root_states (LR:718-820)
+        base = torch.tensor(rs.base_init_state, device=self.device)
+        self.root_states[env_ids] = base
+        self.root_states[env_ids, :3] += self.env_origins[env_ids]
+        if custom_origins:
+            pr = rs.base_init_pos_range
+            if pr is not None:
+                self.root_states[env_ids, 0] += rng(24, pr["x"])
+                self.root_states[env_ids, 1] += rng(25, pr["y"])
+                self.root_states[env_ids, 2] += rng(26, pr["z"])
+            else:
+                self.root_states[env_ids, 0] += rng(24, (-1.0, 1.0))
+                self.root_states[env_ids, 1] += rng(25, (-1.0, 1.0))
+        rr = rs.base_init_rot_range
+        if rr is not None:
+            roll, pitch, yaw = rng(27, rr["roll"]), rng(28, rr["pitch"]), rng(29, rr.get("yaw", [-np.pi, np.pi]))
+            cy, sy = torch.cos(yaw * 0.5), torch.sin(yaw * 0.5)
+            cr_, sr = torch.cos(roll * 0.5), torch.sin(roll * 0.5)
+            cp, sp = torch.cos(pitch * 0.5), torch.sin(pitch * 0.5)
+            self.root_states[env_ids, 3:7] = torch.stack([cy * sr * cp - sy * cr_ * sp, cy * cr_ * sp + sy * sr * cp,
+                                                          sy * cr_ * cp - cy * sr * sp, cy * cr_ * cp + sy * sr * sp], dim=-1)
+        vr = rs.base_init_vel_range if rs.base_init_vel_range is not None else (-0.5, 0.5)
+        for k, ax in enumerate(("x", "y", "z", "roll", "pitch", "yaw")):
+            self.root_states[env_ids, 7 + k] = rng(30 + k, vr[ax] if isinstance(vr, dict) else vr)
+        self.resample_commands(env_ids, u, rs)
+        if rs.randomize_kp:
+            self.Kp_factors[env_ids, 0] = rng(40, rs.kp_range)
+        if rs.randomize_kd:
+            self.Kd_factors[env_ids, 0] = rng(41, rs.kd_range)
+        if rs.randomize_motor_strength:
+            self.motor_strength_factors[env_ids, 0] = rng(42, rs.motor_strength_range)
 
     def snapshot(self) -> Dict[str, torch.Tensor]:
         """Everything a parity test compares, as detached CPU tensors."""

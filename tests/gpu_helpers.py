@@ -29,7 +29,13 @@ def make_env(cfg, state, hf, targets=None, noise=None, no_reset=False, device="c
                 return
             super().reset_idx(ids)
 
+        def _pre_step_callbacks(self):
+            # these tests replay the step without its RNG-driven callbacks (pre-step command resampling,
+            # disturbances; LR:612-613,631-632) -- tests/test_gpu_reset.py covers those
+            return None
+
     env = Env(cfg, state, hf, device=device)
+    env.push_interval = 0                       # no pushes (LR:627-628) in the replayed step either
     env._no_reset = no_reset or targets is None
     env._t = {k: v.to(device) for k, v in (targets or {}).items()}
     if noise is not None:

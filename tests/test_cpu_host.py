@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(raw, name), f"{name} declared in include/himloco_b200.h but not exported"
     assert declared == set(L.EXPORTS), (declared ^ set(L.EXPORTS))
-    assert L.lib.hl_version() == 101
+    assert L.lib.hl_version() == 102
     assert L.lib.hl_sizeof_cfg() == ctypes.sizeof(L.HlCfg)
     assert L.lib.hl_sizeof_env_buffers() == ctypes.sizeof(L.HlEnvBuffers)
 
@@ -151,6 +151,8 @@ def test_presets_equal_the_reference_config_classes(task):
     assert list(na) == list(nb) and np.array_equal(np.asarray(sa), np.asarray(sb))
     assert list(a.episode_sum_names()) == list(b.episode_sum_names())
     assert np.array_equal(np.asarray(a.noise_scale_vec()), np.asarray(b.noise_scale_vec()))
+    import dataclasses
+    assert dataclasses.asdict(a.reset) == dataclasses.asdict(b.reset)        # reset_idx / resampling / domain-rand ranges
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/legged_gym"), reason="needs the reference's URDF (build container only)")

@@ -148,3 +148,25 @@ def test_amp_pairs_and_reward():
     r = O.amp_reward_from_logit(torch.from_numpy(gold["disc_d"]), torch.from_numpy(gold["disc_task_r"]),
                                 0.01, 0.3)
     np.testing.assert_array_equal(r.numpy(), gold["disc_r"])
+
+
+@pytest.mark.parametrize("case", __import__("oracle.make_goldens", fromlist=["RESET_CASES"]).RESET_CASES, ids=lambda c: c["name"])
+def test_oracle_reset_idx_reproduces_the_reference(case):
+    """reset_idx with its draws (LR:288-361): the fixtures come from the reference's own reset_idx with
+    torch_rand_float / rand_like / randint_like fed from a (N, 44) uniform table in call order; the restatement
+    consuming the same table by column must give the same rows."""
+    from oracle.make_goldens import reset_inputs, input_checksum
+    from oracle import torch_oracle as O
+    gold = load_golden(f"reset_{case['name']}.npz")
+    cfg, hf, state, u, ter, ids = reset_inputs(case)
+    # (sums of doubles: the summation order depends on the thread count, hence isclose)
+    assert np.isclose(input_checksum(state), gold["input_checksum"], rtol=1e-12) and np.isclose(float(u.double().sum()), float(gold["u_checksum"]), rtol=1e-12)
+    np.testing.assert_array_equal(ids.numpy(), gold["ids"])
+    env = O.OracleEnv(cfg, state, hf)
+    env.env_origins = ter["env_origins"].clone()
+    terrain = dict(origins=ter["origins"], types=ter["types"], max_level=cfg.num_rows, env_length=cfg.terrain_length,
+                   max_episode_length_s=cfg.episode_length_s)
+    env.reset_idx_draw(ids, u, custom_origins=True, terrain=terrain)
+    np.testing.assert_array_equal(env.terrain_levels.numpy(), gold["terrain_levels"])
+    for k in ("root_states", "dof_state", "commands", "Kp_factors", "Kd_factors", "motor_strength_factors", "env_origins"):
+        np.testing.assert_allclose(getattr(env, k).numpy().reshape(gold[k].shape), gold[k], rtol=1e-6, atol=1e-7, err_msg=k)
