@@ -33,6 +33,23 @@ import torch  # noqa: E402
 METRIC = "post_physics_gae_env_steps_per_s"
 UNIT = "env-steps/s"
 AC_PARAMS = 545_660          # HIMActorCritic incl. estimator
+EST_PARAMS = 59_875          # HIMEstimator's own optimiser step (him_estimator.py:111-114)
+DISC_PARAMS = 587_777        # AMPDiscriminator (hybrid_ppo.py:271)
+
+
+def bind_to_gpu_numa(local_rank):
+    """Pin this process to the CPUs of the GPU's NUMA node (NVML's ideal affinity) so pinned staging buffers and the
+    copy-issuing thread are socket-local.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local_rank])
+                                              if os.environ.get("CUDA_VISIBLE_DEVICES") else local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return {"cpus": len(cpus), "first": cpus[0], "last": cpus[-1]}
+    except Exception as ex:  # pragma: no cover
+        return {"error": str(ex)[:80]}
 
 
 def peaks():
@@ -82,19 +99,65 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------- CPU arm (oracle port)
+# ----------------------------------------------------------------------------- CPU arm
+def _reference_root():
+    """Where the reference's own Python sources are, if anywhere (this container: /root/reference; the GPU box has
+    neither -- the reference needs the proprietary isaacgym wheel and is not pip-installable: DESIGN.md §7)."""
+    for cand in (os.environ.get("HIMLOCO_REFERENCE_ROOT"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "legged_gym", "legged_gym")) and os.path.isdir(os.path.join(cand, "rsl_rl", "rsl_rl")):
+            return cand
+    return None
+
+
 def cpu_rollout_runner(n_envs, t_len, seed=1234):
-    """The reference's torch implementation of the path, restated (oracle/torch_oracle.py; the
-    Python reference itself cannot travel to the GPU box), on all host cores.  Returns a callable
-    running ONE rollout (T x {4 torques, post_physics_step} + compute_returns)."""
+    """The reference's torch implementation of the path on all host cores: the reference's OWN classes under the
+    stub harness (oracle/ref_harness.py) when its sources are present (kind "reference"), else the restatement
+    oracle/torch_oracle.py (kind "port": the Python reference cannot travel to the GPU box).  Returns
+    (callable running ONE rollout = T x {4 torques, post_physics_step} + compute_returns, threads, kind)."""
     from isaacgymloco_b200 import config as C, synthetic as S
-    from oracle import torch_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = C.aliengo("flat", num_envs=n_envs, index_math=C.INDEX_MATH_TORCH_CPU)
     hf = S.make_terrain(cfg, seed=1)
     state = S.make_state(cfg, n_envs, hf, seed=seed)
-    env = O.OracleEnv(cfg, state, hf)
     roll = S.make_rollout(n_envs, t_len, seed)
+    ref_root = _reference_root()
+    if ref_root is not None:
+        try:
+            os.environ["HIMLOCO_REFERENCE_ROOT"] = ref_root
+            import types
+            from oracle import ref_harness as H
+            H.REFERENCE_ROOT = ref_root
+            env = H.build_reference_env("flat", state, hf, sum_names=cfg.episode_sum_names(), hot_cfg=cfg)
+            from rsl_rl.storage import HIMRolloutStorage as RefStorage
+            rc = env.cfg
+            env.custom_origins = True
+            env.env_origins = torch.zeros(n_envs, 3)
+            env.terrain_origins = torch.zeros(cfg.num_rows, cfg.num_cols, 3)
+            env.terrain_types = torch.zeros(n_envs, dtype=torch.long)
+            env.max_terrain_level = cfg.num_rows
+            env.base_init_state = torch.tensor(rc.init_state.pos + rc.init_state.rot + rc.init_state.lin_vel + rc.init_state.ang_vel,
+                                               dtype=torch.float)
+            noop = lambda self, *a, **k: None
+            # PhysX-facing / host-curriculum hooks are outside the path (and need a live sim): no-ops, as on the GPU arm
+            for name in ("refresh_actor_rigid_shape_props", "update_command_curriculum", "_push_robots", "_disturbance_robots"):
+                setattr(env, name, types.MethodType(noop, env))
+            st = RefStorage(n_envs, t_len, [270], [238], [12], "cpu")
+            st.rewards.copy_(roll["rewards"]); st.values.copy_(roll["values"]); st.dones.copy_(roll["dones"])
+            delayed = env.actions.view(n_envs, 1, 12).repeat(1, 4, 1)
+
+            def one_rollout_ref():
+                for _ in range(t_len):
+                    for k in range(4):
+                        env.torques = env._compute_torques(delayed[:, k]).view(env.torques.shape)
+                    env.post_physics_step()
+                st.compute_returns(roll["last_values"], 0.99, 0.95)
+
+            one_rollout_ref()
+            return one_rollout_ref, torch.get_num_threads(), "reference"
+        except Exception as ex:  # pragma: no cover
+            sys.stderr.write(f"[bench] reference under the stub harness failed ({type(ex).__name__}: {ex}); timing the port\n")
+    from oracle import torch_oracle as O
+    env = O.OracleEnv(cfg, state, hf)
     delayed = env.actions.view(n_envs, 1, 12).repeat(1, 4, 1)
 
     def one_rollout():
@@ -106,15 +169,18 @@ def cpu_rollout_runner(n_envs, t_len, seed=1234):
             env.post_physics_step(noise, None)
         O.compute_returns(roll["rewards"], roll["values"], roll["dones"], roll["last_values"], 0.99, 0.95)
 
-    return one_rollout, torch.get_num_threads()
+    return one_rollout, torch.get_num_threads(), "port"
+
+
+CPU_SAMPLE_ENVS = 4096      # bounded sample of the workload for the CPU arms (configs[0]: the reference's own CPU-runnable case)
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_envs, t_len = 4096, args.rollout
-    fn, cores = cpu_rollout_runner(n_envs, t_len)
+    n_envs, t_len = CPU_SAMPLE_ENVS, args.rollout
+    fn, cores, kind = cpu_rollout_runner(n_envs, t_len)
     for _ in range(args.warmup):
         fn()
     t0 = time.perf_counter()
@@ -122,13 +188,17 @@ def run_reference_arm(args):
         fn()
     dt = time.perf_counter() - t0
     value = n_envs * t_len * args.steps / dt
-    sample = f"{n_envs} of {args.envs} envs x {t_len}-step rollout per step (oracle/torch_oracle.py, torch CPU)"
+    src = "the reference's own LeggedRobot / HIMRolloutStorage under oracle/ref_harness.py" if kind == "reference" else "oracle/torch_oracle.py"
+    sample = (f"each step = one {t_len}-step rollout of {n_envs} envs (a {n_envs}-of-{args.envs} env sample of the workload; "
+              f"throughput per env-step is size-independent on the CPU), {src}, torch CPU, {cores} threads")
+    cfgd = workload_config(args, world=args.gpus)
+    cfgd["sample_envs"] = n_envs
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, world=args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": cfgd,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -147,12 +217,12 @@ def workload_config(args, world):
 
 # ----------------------------------------------------------------------------- GPU arm
 class Workload:
-    def __init__(self, envs, t_len, rank, world, device, seed=1234):
+    def __init__(self, envs, t_len, rank, world, device, seed=1234, task="flat"):
         from isaacgymloco_b200 import config as C, synthetic as S
         from isaacgymloco_b200.legged_robot import FusedLeggedRobot
         from isaacgymloco_b200.rollout_storage import HIMRolloutStorage
         self.envs, self.t_len, self.world, self.device = envs, t_len, world, device
-        self.cfg = C.aliengo("flat", num_envs=envs * world, env_id_offset=rank * envs)
+        self.cfg = C.aliengo(task, num_envs=envs * world, env_id_offset=rank * envs)
         # the torch-RNG / PhysX-facing interval hooks (pushes, disturbances, the host-side command curriculum) are
         # outside the path; everything else of post_physics_step runs, reset_idx included
         self.cfg.reset.push_robots = False
@@ -189,10 +259,10 @@ class Workload:
             env._fused_event_hook = hook
         else:
             env._fused_event_hook = None
-        # the whole of post_physics_step as one chain of launches, no host sync: pre-step command resampling, the fused
-        # kernel, reset ids + terminal rows, episode logging means, reset_idx (Philox re-draws) + post-reset fix-up
+        # the whole of post_physics_step as one chain of launches, no host sync: the fused kernel (pre-step command resampling folded in),
+        # reset ids + terminal rows, then ONE launch for reset_idx (Philox re-draws, episode-logging means) + post-reset fix-up
         env.post_physics_step_device()
-        self.launches += env.cfg_hot.decimation + (4 if env.single_launch else 5)
+        self.launches += env.cfg_hot.decimation + (2 if env.single_launch else 3)
 
     def rollout(self, time_fused=False, finish=True):
         for _ in range(self.t_len):
@@ -238,21 +308,39 @@ def run_gpu_arm(args):
         args.gpus = world
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa(local)           # before any pinned allocation: H2D/D2H staging stays on the GPU's socket
     wl = Workload(args.envs, args.rollout, rank, world, device)
     bytes_tab = R.per_env_step_bytes(wl.cfg, args.rollout)
 
-    # multi-GPU exchange: 20 flat-gradient all-reduces per update on a side stream (synthetic grads)
-    comm_stream = torch.cuda.Stream() if world > 1 else None
-    grads = torch.randn(AC_PARAMS, device=device) if world > 1 else None
+    # multi-GPU exchange steps of one PPO update, on a side stream, synthetic payloads of the real sizes:
+    # per minibatch (5 epochs x 4) the estimator's own step (him_estimator.py:111-114, 59,875 fp32), the flat
+    # HIMActorCritic gradient (him_ppo.py:182, 545,660 fp32) and the adaptive-KL scalar (him_ppo.py:148); with --amp
+    # also the discriminator gradient (hybrid_ppo.py:271, 587,777 fp32) and the 61-double normaliser merge
+    # (hybrid_ppo.py:279-281).  The 3-double advantage moments ride inside the rollout (storage.normalize_advantages).
+    comm_stream = torch.cuda.Stream() if world > 1 and not args.no_comm else None
+    if comm_stream is not None:
+        grads = torch.randn(AC_PARAMS, device=device)
+        est_grads = torch.randn(EST_PARAMS, device=device)
+        kl = torch.zeros(1, device=device)
+        disc_grads = torch.randn(DISC_PARAMS, device=device) if args.amp else None
+        norm_stats = torch.zeros(61, dtype=torch.float64, device=device) if args.amp else None
+
+    def exchange():
+        for _ in range(20):
+            dist.all_reduce(est_grads, op=dist.ReduceOp.AVG)
+            dist.all_reduce(grads, op=dist.ReduceOp.AVG)
+            dist.all_reduce(kl, op=dist.ReduceOp.AVG)
+            if args.amp:
+                dist.all_reduce(disc_grads, op=dist.ReduceOp.AVG)
+                dist.all_reduce(norm_stats, op=dist.ReduceOp.SUM)
 
     def step():
-        if world > 1:
+        if comm_stream is not None:
             comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(comm_stream):
-                for _ in range(20):
-                    dist.all_reduce(grads, op=dist.ReduceOp.AVG)
+                exchange()
         wl.rollout(time_fused=True)
-        if world > 1:
+        if comm_stream is not None:
             torch.cuda.current_stream().wait_stream(comm_stream)
 
     for _ in range(max(args.warmup, 3)):
@@ -280,26 +368,33 @@ def run_gpu_arm(args):
             with torch.cuda.stream(s):
                 wl.rollout()
                 torch.cuda.synchronize()
-                with torch.cuda.graph(g, stream=s):
-                    wl.rollout(finish=(world == 1))     # the NCCL all-reduce stays outside the graph
+                moments_in_graph = True
+                try:
+                    with torch.cuda.graph(g, stream=s):
+                        wl.rollout(finish=True)          # world > 1: the 3-double moments all-reduce (NCCL) is captured too
+                except Exception:
+                    moments_in_graph = False             # NCCL build that cannot be captured: keep that one collective outside
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=s):
+                        wl.rollout(finish=(world == 1))
             torch.cuda.current_stream().wait_stream(s)
 
             def graph_step():
-                if world > 1:
+                if comm_stream is not None:
                     comm_stream.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(comm_stream):
-                        for _ in range(20):
-                            dist.all_reduce(grads, op=dist.ReduceOp.AVG)
+                        exchange()
                 g.replay()
-                if world > 1:
+                if world > 1 and not moments_in_graph:
                     wl.finish()
+                if comm_stream is not None:
                     torch.cuda.current_stream().wait_stream(comm_stream)
 
             for _ in range(3):
                 graph_step()
             gms = timed(graph_step, args.steps, world > 1)
             graph_info = {"value": world * args.envs * args.rollout * args.steps / (gms * 1e-3), "unit": UNIT,
-                          "ms_per_step": gms / args.steps}
+                          "ms_per_step": gms / args.steps, "moments_allreduce_in_graph": bool(moments_in_graph) if world > 1 else None}
             if gms < ms_direct:
                 ms, mode = gms, "cuda_graph_replay"
         except Exception as ex:  # pragma: no cover
@@ -325,7 +420,11 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
-        "gpu_launches": launches, "roofline": roofline, "timing_mode": mode,
+        "gpu_launches": launches, "roofline": roofline, "timing_mode": mode, "cpu_affinity": affinity,
+        "exchange": None if world == 1 else ("off (--no-comm)" if args.no_comm else
+                                             "20 x {estimator 59,875 + actor-critic 545,660 fp32 grads + KL scalar}" +
+                                             (" + {discriminator 587,777 fp32 + 61-double normaliser}" if args.amp else "") +
+                                             " all-reduces per rollout on a side stream; 3-double advantage moments inside the rollout"),
         "direct_launch": {"value": world * args.envs * args.rollout * args.steps / (ms_direct * 1e-3), "unit": UNIT,
                           "ms_per_step": ms_direct / args.steps},
     }
@@ -342,25 +441,33 @@ def run_gpu_arm(args):
             line["latency_4096"] = measure_latency_4096(args)
             line["next_rows"] = {"record_transition": measure_record_transition(args, peak),
                                  "minibatch_gather": measure_minibatch_gather(args, peak)}
+            line["other_configs"] = {"stairs16384": measure_stairs16384(args, peak), "amp16384": measure_amp16384(args, peak)}
         if not args.no_cpu:
-            fn, cores = cpu_rollout_runner(4096, args.rollout)
+            fn, cores, kind = cpu_rollout_runner(CPU_SAMPLE_ENVS, args.rollout)
             fn()
             t0 = time.perf_counter()
             reps = 3
             for _ in range(reps):
                 fn()
             dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": 4096 * args.rollout * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{reps} rollouts of 4096 envs x {args.rollout} steps (configs[0]) after 1 warm-up, "
-                                              f"oracle/torch_oracle.py on torch CPU"}
+            line["cpu_baseline"] = {"value": CPU_SAMPLE_ENVS * args.rollout * reps / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{reps} rollouts of {CPU_SAMPLE_ENVS} envs x {args.rollout} steps (configs[0]) after 1 warm-up, "
+                                              + ("the reference's own classes under oracle/ref_harness.py" if kind == "reference"
+                                                 else "oracle/torch_oracle.py") + " on torch CPU"}
     print(json.dumps(line), flush=True)
 
 
 def measure_e2e(wl, args, world):
     import torch.distributed as dist
     env = wl.env
-    names_in = ("root_states", "dof_state", "contact_forces", "rigid_body_states", "actions")
-    host_in = {k: wl.host_state[k].contiguous().pin_memory() for k in names_in}
+    # the host ships the four foot records packed ((N,4,13): 208 B/env) instead of all 17 bodies (884 B/env)
+    names_in = ("root_states", "dof_state", "contact_forces", "foot_records", "actions")
+    nb = env.num_bodies
+    feet = wl.host_state["rigid_body_states"].view(-1, nb, 13)[:, list(wl.cfg.feet_indices), :].contiguous()
+    env.foot_records = feet.to(env.device)
+    env.refresh_buffers()
+    host_src = dict(wl.host_state, foot_records=feet)
+    host_in = {k: host_src[k].contiguous().pin_memory() for k in names_in}
     dev_in = {k: getattr(env, k) for k in names_in}
     outs = {"obs_buf": env.obs_buf, "privileged_obs_buf": env.privileged_obs_buf, "rew_buf": env.rew_buf, "reset_buf": env.reset_buf}
     host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outs.items()}
@@ -406,7 +513,8 @@ def measure_e2e(wl, args, world):
     ms = timed(e2e_rollout, iters, world > 1)
     return {"value": world * args.envs * wl.t_len * iters / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * wl.t_len,
             "d2h_bytes_per_step": d2h * wl.t_len, "rollouts": iters, "ms_per_step": ms / iters,
-            "api": "FusedLeggedRobot._compute_torques x4 + post_physics_step per env-step, HIMRolloutStorage.compute_returns per rollout"}
+            "api": "FusedLeggedRobot._compute_torques x4 + post_physics_step per env-step, HIMRolloutStorage.compute_returns per rollout",
+            "h2d_per_env": h2d // args.envs, "d2h_per_env": d2h // args.envs}
 
 
 def measure_record_transition(args, peak_gbs):
@@ -467,6 +575,109 @@ def measure_minibatch_gather(args, peak_gbs):
             "frac": gbs / peak_gbs, "torch_index_us_per_minibatch": 1e3 * ms_t}
 
 
+def measure_stairs16384(args, peak_gbs):
+    """BASELINE.json configs[2]: aliengo_stairs, 16,384 envs, 1300 x 2300 synthetic stair /
+    slope / rough field, the 20-term stairs reward set + termination, all five termination clauses.  16,384 envs touch
+    81 MB per env-step -- less than the 126 MB L2 -- so 277 MB are written between timed replays to flush it."""
+    from isaacgymloco_b200 import roofline as R
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n = 16384
+    wl = Workload(n, args.rollout, 0, 1, dev, task="stairs")
+    bytes_tab = R.per_env_step_bytes(wl.cfg, args.rollout)
+    flush = torch.empty(277 * 1024 * 1024 // 4, device=dev)
+    for _ in range(2):
+        wl.rollout()
+    # direct launches with an L2 flush before every env-step: CUDA-event pairs around the fused kernel
+    wl.fused_ms.clear()
+    for _ in range(8):
+        flush.fill_(1.0)
+        wl.env_step(time_fused=True)
+    torch.cuda.synchronize()
+    fus = [a.elapsed_time(b) for a, b in wl.fused_ms][2:]
+    fused_ms = sum(fus) / len(fus)
+    wl.env._fused_event_hook = None
+    g = torch.cuda.CUDAGraph()
+    s_ = torch.cuda.Stream()
+    s_.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s_):
+        wl.rollout()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s_):
+            wl.rollout()
+    torch.cuda.current_stream().wait_stream(s_)
+    for _ in range(3):
+        g.replay()
+    iters = 10
+    ms = timed(g.replay, iters, False) / iters
+    alg = bytes_tab["post_physics"] * n
+    gbs = alg / (fused_ms * 1e-3) / 1e9
+    return {"workload": "aliengo_stairs, 16384 envs x 24-step rollout, 21-row stairs reward set, 187-pt scan on the 1300x2300 field",
+            "value": n * args.rollout / (ms * 1e-3), "unit": UNIT, "ms_per_rollout_graph": ms, "l2_policy": "fused-kernel timing: 277 MB flush "
+            "write before every env-step; rollout value: graph replay, 81 MB working set (L2-resident)",
+            "roofline": {"bound": "hbm", "kernel": "hl_post_physics_fused_kernel", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": gbs / peak_gbs, "avg_launch_ms": fused_ms, "algorithmic_bytes_per_launch": alg,
+                         "bytes_per_env_step": bytes_tab}}
+
+
+def measure_amp16384(args, peak_gbs):
+    """BASELINE.json configs[3]: the 7 aliengo clips (from tests/golden/amp.npz: the mocap
+    files live in the reference tree), 16,384 samples per get_full_frame_at_time_batch, a 2e6-transition preload,
+    expert-pair gathers of 16384*24/4 rows, discriminator-input assembly + reward epilogue for 16,384 envs; the MLP
+    (cuBLAS) is timed separately."""
+    import numpy as np
+    from isaacgymloco_b200.amp_discriminator import AMPDiscriminator, Normalizer
+    from isaacgymloco_b200.motion_loader import AMPLoader
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "amp.npz"), allow_pickle=False))
+    k = len(gold["frame_durations"])
+    tabs = dict(frames=[gold[f"clip{i}"] for i in range(k)], frame_durations=gold["frame_durations"], weights=gold["weights_raw"],
+                names=[str(x) for x in gold["clip_names"]])
+    np.random.seed(0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ld = AMPLoader(str(dev), 0.02, preload_transitions=True, num_preload_transitions=2_000_000, clip_tables=tabs)
+    torch.cuda.synchronize()
+    preload_s = time.perf_counter() - t0
+    n = 16384
+    idx = ld.weighted_traj_idx_sample_batch(n)
+    tm = ld.traj_time_sample_batch(idx)
+    idx_t, tm_t = torch.as_tensor(idx).to(dev), torch.as_tensor(tm).to(dev)
+    blend = lambda: ld.get_full_frame_at_time_batch_device(idx_t, tm_t)
+    for _ in range(3):
+        blend()
+    ms_blend = timed(blend, 50, False) / 50
+    mb = n * 24 // 4
+    pidx = torch.as_tensor(np.random.choice(ld.preloaded_s.shape[0], size=mb)).to(dev)
+    pairs = lambda: ld.gather_pairs(pidx)
+    for _ in range(3):
+        pairs()
+    ms_pairs = timed(pairs, 50, False) / 50
+    torch.manual_seed(0)
+    disc = AMPDiscriminator(60, 0.01, [1024, 512], str(dev), task_reward_lerp=0.3).to(dev)
+    norm = Normalizer(30, device=str(dev))
+    s0, s1 = ld.gather_pairs(pidx[:n])
+    norm.update(s0)
+    task_r = torch.rand(n, device=dev)
+    asm = lambda: disc.assemble_input(s0, s1, norm)
+    full = lambda: disc.predict_amp_reward(s0, s1, task_r, normalizer=norm)
+    for _ in range(3):
+        asm(); full()
+    ms_asm = timed(asm, 50, False) / 50
+    ms_full = timed(full, 50, False) / 50
+    gb = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9
+    return {"workload": "aliengo AMP: 7 clips / 658 frames, 16384-sample frame blend, 2e6 preload, 98304-row pair gather, 16384-env "
+                        "discriminator input + reward",
+            "frame_blend": {"samples": n, "us": 1e3 * ms_blend, "samples_per_s": n / (ms_blend * 1e-3),
+                            "GBps_written": gb(n * 49 * 4, ms_blend), "note": "table (129 KB) is L2/L1-resident; output 3.2 MB"},
+            "preload_2e6": {"seconds": preload_s, "note": "host numpy sampling (RNG, as in the reference) + 2 blend launches of 2e6 samples"},
+            "pair_gather": {"rows": mb, "us": 1e3 * ms_pairs, "GBps": gb(mb * (2 * 30 * 4 + 2 * 30 * 4 + 8), ms_pairs),
+                            "frac_of_hbm_peak": gb(mb * (2 * 30 * 4 + 2 * 30 * 4 + 8), ms_pairs) / peak_gbs,
+                            "note": "random 196-B rows of two 392 MB tables: sector-granular gathers (algorithmic bytes counted, not sectors)"},
+            "disc_input": {"envs": n, "us": 1e3 * ms_asm, "GBps": gb(n * (60 * 4 + 60 * 4), ms_asm)},
+            "predict_amp_reward": {"envs": n, "us_total": 1e3 * ms_full, "us_mlp_cublas": 1e3 * (ms_full - ms_asm),
+                                   "note": "assembly + 60-1024-512-1 MLP (cuBLAS, out of scope) + reward epilogue"}}
+
+
 def measure_latency_4096(args):
     """configs[1]: 4096 envs on one B200 -- the working set (20 MB) is L2-resident, so this is a
     latency number (CUDA-graph replay of one rollout), not a roofline one."""
@@ -503,6 +714,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-comm", action="store_true", help="N>1: leave out the gradient / statistics exchanges (attribution runs)")
+    ap.add_argument("--amp", action="store_true", help="N>1: add the AMP discriminator-gradient and normaliser exchanges")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -110,6 +110,7 @@ typedef struct HlCfg {
 /* Device buffers of one env shard, named after the LeggedRobot attributes they are. */
 #define HL_BUF_HISTORY_CLIPPED 1u /* obs_buf_in already lies within +-clip_observations (true after any step) */
 
+struct HlReset;
 typedef struct HlEnvBuffers {
   int32_t struct_bytes;
   uint32_t flags;                 /* HL_BUF_* */
@@ -169,6 +170,14 @@ typedef struct HlEnvBuffers {
   const float* term_noise_u187;
   uint64_t* fused_ws;             /* hl_fused_workspace_bytes(N) bytes, zeroed ONCE at allocation; also the tile
                                    * ticket of the persistent fused kernel (NULL => the tiled fallback kernel runs) */
+  const float* foot_records;      /* optional (N,4,13): the four foot body-state records packed (what a host that ships PhysX
+                                   * state over PCIe should send: 208 B/env instead of the 884 B of rigid_body_states);
+                                   * when non-NULL it replaces rigid_body_states[:, feet_idx] */
+  const struct HlReset* resample_host; /* HOST pointer or NULL: when set (with resample_interval > 0) the fused step itself resamples
+                                   * the commands of the envs whose incremented episode length is a multiple of the interval
+                                   * (_post_physics_step_callback, LR:612-613) before the heading command: ranges / uniforms
+                                   * are read from this struct at launch time (Philox stream 2 when uniforms is NULL) */
+  int64_t resample_interval;
   const float* height_min3f;      /* (rows-1,cols-1) fp32 = min3 * vertical_scale from hl_terrain_prepare_f32; may be
                                    * NULL (then the fused step uses the tiled fallback kernel and height_min3) */
 } HlEnvBuffers;
@@ -294,6 +303,11 @@ typedef struct HlReset {
   float* kd_factors;               /* (N,1) or NULL */
   float* motor_strength_factors;   /* (N,1) or NULL */
   const float* uniforms;           /* (N, HL_RESET_NU) pre-drawn U[0,1) or NULL => Philox stream 3 */
+  /* optional episode logging of reset_idx (LR:346-350) folded into the reset launch: means_out[k] = mean over the reset
+   * envs of episode_sums[k] / clip(episode_length, 1) / dt, unchanged when no env resets.  means_ws: (n_rows + 1)
+   * doubles, zeroed ONCE at allocation (the kernel re-arms it). */
+  float* means_out;                /* (n_rows,) or NULL */
+  double* means_ws;
 } HlReset;
 int hl_sizeof_reset(void);
 /* reset_idx(env_ids) without the fix-up: curriculum, state re-draws, the RNG-free buffer resets (LR:323-329,361). */

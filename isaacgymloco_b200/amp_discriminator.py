@@ -100,6 +100,17 @@ class AMPDiscriminator(nn.Module):
         """x = cat(normalise(state), normalise(next_state')) (N,60) with next_state' rows of the
         reset envs replaced by their terminal AMP states (hybrid_runner.py:191-192)."""
         n = state.shape[0]
+        # the kernel is written for the reference's AMP observation (LR:416: 30 columns, 60-wide discriminator input)
+        if state.dim() != 2 or state.shape[1] != 30 or tuple(next_state.shape) != tuple(state.shape):
+            raise ValueError(f"assemble_input: state / next_state must be (N, 30), got {tuple(state.shape)} / {tuple(next_state.shape)}")
+        if self.input_dim != 60:
+            raise ValueError(f"assemble_input: discriminator input_dim must be 60, is {self.input_dim}")
+        if state.dtype != torch.float32 or next_state.dtype != torch.float32 or not state.is_cuda or not next_state.is_cuda:
+            raise ValueError("assemble_input: float32 CUDA tensors required")
+        if normalizer is not None and int(getattr(normalizer, "dim", 30)) != 30:
+            raise ValueError("assemble_input: the normaliser must have 30 columns")
+        if terminal_states is not None and (terminal_states.dim() != 2 or terminal_states.shape[1] != 30):
+            raise ValueError("assemble_input: terminal_states must be (n_reset, 30)")
         state = state.contiguous()
         next_state = next_state.contiguous()
         x = torch.empty(n, 60, device=state.device)

@@ -147,7 +147,7 @@ class HlReset(ctypes.Structure):
         ("cmd_heading", ctypes.c_float * 2), ("high_vel_frac", ctypes.c_float), ("env_length", ctypes.c_float),
         ("max_episode_length_s", ctypes.c_float)] + [(n, ctypes.c_void_p) for n in (
         "root_states", "dof_state", "commands", "env_origins", "terrain_origins", "terrain_levels", "terrain_types",
-        "kp_factors", "kd_factors", "motor_strength_factors", "uniforms")]
+        "kp_factors", "kd_factors", "motor_strength_factors", "uniforms", "means_out", "means_ws")]
 
 
 def _f32(x) -> float:

@@ -340,9 +340,9 @@ __device__ __forceinline__ void hl_stage_env(float* st, const HlCfg& c, const Hl
   const float r_root = (lane < 13 && b.root_states) ? b.root_states[e * 13 + lane] : 0.0f;
   const float r_dof = (lane < 24 && b.dof_state) ? b.dof_state[e * 24 + lane] : 0.0f;
   float r_feet = 0.0f;
-  if (lane < 24 && b.rigid_body_states) {
+  if (lane < 24 && (b.rigid_body_states || b.foot_records)) {
     const int f = lane / 6, k = lane - f * 6;
-    r_feet = b.rigid_body_states[(e * B + c.feet_idx[f]) * 13 + (k < 3 ? k : k + 4)];
+    r_feet = hl_foot_rec(c, b, e, f)[k < 3 ? k : k + 4];
   }
   const float* a_src[7] = {b.actions, b.last_actions, b.last_last_actions, b.last_dof_pos, b.last_dof_vel, b.torques, b.last_torques};
   float r_a[7];
@@ -562,8 +562,30 @@ __global__ void __launch_bounds__(256, 3) hl_stage_kernel(HlCfg c, HlEnvBuffers 
         b.last_torques[e * 12 + lane] = 0.0f;
       }
       if (lane < 4) b.feet_air_time[e * 4 + lane] = 0.0f;
-      if (b.episode_sums)
+      if (b.episode_sums) {
+        if ((stages & HL_ST_RESET_DRAW) && rs.means_out && rs.means_ws) {   // LR:346-350: the logged means, before the rows are zeroed
+          const long long len = b.episode_length_buf[e] < 1 ? 1 : b.episode_length_buf[e];
+          for (int k = lane; k < c.n_terms + c.has_termination_term; k += 32)
+            atomicAdd(rs.means_ws + k, (double)__fdiv_rn(__fdiv_rn(b.episode_sums[(long long)k * n + e], (float)len), c.dt));
+          // the warp that completes the list turns the sums into means and re-arms the workspace (graph safe)
+          const int R = c.n_terms + c.has_termination_term;
+          __threadfence();
+          __syncwarp();
+          unsigned long long done = 0;
+          if (lane == 0) done = atomicAdd(reinterpret_cast<unsigned long long*>(rs.means_ws + R), 1ull) + 1ull;
+          done = __shfl_sync(0xffffffffu, done, 0);
+          if (done == (unsigned long long)items) {
+            __threadfence();
+            for (int k = lane; k < R; k += 32) {
+              const double t = *reinterpret_cast<volatile double*>(rs.means_ws + k);
+              rs.means_out[k] = (float)(t / (double)items);
+              rs.means_ws[k] = 0.0;
+            }
+            if (lane == 0) *reinterpret_cast<unsigned long long*>(rs.means_ws + R) = 0ull;
+          }
+        }
         for (int k = lane; k < c.n_terms + c.has_termination_term; k += 32) b.episode_sums[(long long)k * n + e] = 0.0f;
+      }
       if (lane == 0) {
         b.episode_length_buf[e] = 0;
         b.reset_buf[e] = 1;
@@ -1345,6 +1367,11 @@ __device__ __forceinline__ float scan_gather_f(const HlCfg& c, const float* __re
 
 struct FusedArgs {
   int cf_stride, need_ldp, need_ltq, want_base;
+  long long rs_interval;  // > 0: resample the commands of envs whose incremented episode length hits the interval (LR:612-613)
+  int rs_heading;
+  double rs_hi_envs;      // num_envs * 0.2 (LR:649)
+  float rs_lin_vel_x[2], rs_lin_vel_y[2], rs_third[2];   // third = heading range (heading_command) or yaw-rate range
+  const float* rs_uniforms;   // (N, HL_RESET_NU) or nullptr => Philox stream 2
   int hist_pf;            // bulk-prefetch the tile's obs-history slab into L2 (obs_buf_in 16-B aligned)
   int tma_ok;             // every dense slab of a full tile is 16-B aligned with a 16-B multiple size (n % 4 == 0, aligned bases)
   int sums_aligned;       // episode_sums rows are 16-B aligned per block (n % 4 == 0, base aligned)
@@ -1352,6 +1379,29 @@ struct FusedArgs {
   int hist_clipped;       // obs history is known to be within +-clip_obs already (every step after the first)
   HlPhiloxKeys keys;      // Philox round keys of bufs.philox_seed (host-computed: constant-bank operands)
 };
+
+// _resample_commands for the lane's env inside the fused step (same arithmetic and uniform columns as hl_resample_kernel)
+__device__ __forceinline__ void hl_fused_resample(const FusedArgs& fa, const HlEnvBuffers& b, long long ge, long long gid, float* cmd) {
+  float u[4];
+  if (fa.rs_uniforms) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = fa.rs_uniforms[ge * HL_RESET_NU + 36 + k];
+  } else {
+    const uint4 q = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)gid, 9u, 2u);
+    u[0] = hl_u01(q.x); u[1] = hl_u01(q.y); u[2] = hl_u01(q.z); u[3] = hl_u01(q.w);
+  }
+  float c0 = (1.0f - (-1.0f)) * u[0] + (-1.0f);
+  float c1 = (fa.rs_lin_vel_y[1] - fa.rs_lin_vel_y[0]) * u[1] + fa.rs_lin_vel_y[0];
+  const float c3 = (fa.rs_third[1] - fa.rs_third[0]) * u[2] + fa.rs_third[0];
+  if ((double)gid < fa.rs_hi_envs) {
+    c0 = (fa.rs_lin_vel_x[1] - fa.rs_lin_vel_x[0]) * u[3] + fa.rs_lin_vel_x[0];
+    c1 *= fabsf(c0) < 1.0f ? 1.0f : 0.0f;
+  }
+  const float keep = sqrtf(c0 * c0 + c1 * c1) > 0.2f ? 1.0f : 0.0f;
+  cmd[0] = c0 * keep;
+  cmd[1] = c1 * keep;
+  cmd[fa.rs_heading ? 3 : 2] = c3;
+}
 
 // tile sizes: 64 (default), 52 (65,536 envs = 1261 CTAs = 2.84 waves of 444 instead of 2.31 -> 3
 // waves of 52 instead of 64 envs), 32 (small shards: more CTAs than SMs sooner)
@@ -1422,7 +1472,7 @@ extern "C" int64_t hl_fused_workspace_bytes(int64_t n) { return (int64_t)(((n + 
 extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, void* stream) {
   if (int r = check_cfg(cfg, bufs)) return r;
   const HlEnvBuffers& b = *bufs;
-  HL_CHECK_ARG(b.root_states && b.dof_state && b.contact_forces && b.rigid_body_states && b.actions && b.last_actions &&
+  HL_CHECK_ARG(b.root_states && b.dof_state && b.contact_forces && (b.rigid_body_states || b.foot_records) && b.actions && b.last_actions &&
                    b.last_last_actions && b.last_dof_pos && b.last_dof_vel && b.torques && b.last_torques &&
                    b.last_root_vel && b.commands && b.episode_length_buf && b.last_contacts && b.contact_filt &&
                    b.feet_air_time && b.disturbance && b.base_lin_vel && b.base_ang_vel && b.projected_gravity &&
@@ -1474,6 +1524,20 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
   {
     bool ok = (n % 4 == 0) && (!b.episode_sums || ((uintptr_t)b.episode_sums & 15) == 0);
     fa.tma_ok = ok;
+    fa.rs_interval = 0;
+    fa.rs_uniforms = nullptr;
+    if (b.resample_host && b.resample_interval > 0) {
+      const HlReset* r = b.resample_host;
+      HL_CHECK_ARG(r->struct_bytes == (int)sizeof(HlReset), "resample_host: HlReset size mismatch");
+      fa.rs_interval = b.resample_interval;
+      fa.rs_heading = r->heading_command;
+      fa.rs_hi_envs = (double)r->num_envs_global * (double)r->high_vel_frac;
+      fa.rs_lin_vel_x[0] = r->cmd_lin_vel_x[0]; fa.rs_lin_vel_x[1] = r->cmd_lin_vel_x[1];
+      fa.rs_lin_vel_y[0] = r->cmd_lin_vel_y[0]; fa.rs_lin_vel_y[1] = r->cmd_lin_vel_y[1];
+      const float* third = r->heading_command ? r->cmd_heading : r->cmd_ang_vel_yaw;
+      fa.rs_third[0] = third[0]; fa.rs_third[1] = third[1];
+      fa.rs_uniforms = r->uniforms;
+    }
     const char* pf = getenv("HL_PK_HIST_PF");   // experiment knob
     fa.hist_pf = (((uintptr_t)b.obs_buf_in & 15) == 0) && !(pf && pf[0] == '0');
   }

@@ -33,6 +33,12 @@ struct EnvScalars {
   bool time_out, reset;
 };
 
+// body-state record (13 floats) of foot f of env e: from the packed (N,4,13) tensor when given, else
+// rigid_body_states[e, feet_idx[f]] (LR:203-204)
+__device__ __forceinline__ const float* hl_foot_rec(const HlCfg& c, const HlEnvBuffers& b, long long e, int f) {
+  return b.foot_records ? b.foot_records + (e * 4 + f) * 13 : b.rigid_body_states + (e * c.num_bodies + c.feet_idx[f]) * 13;
+}
+
 // ----------------------------------------------------------------------------- frame
 // isaacgym.torch_utils.quat_rotate_inverse: a - b + c with a = v(2w^2-1), b = 2w(q_v x v),
 // c = 2 q_v (q_v . v)   (used at LR:198-200,1616,1691-1692)

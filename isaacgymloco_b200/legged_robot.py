@@ -219,6 +219,7 @@ class FusedLeggedRobot:
         p = L.ptr
         b.root_states, b.dof_state = p(self.root_states), p(self.dof_state)
         b.contact_forces, b.rigid_body_states = p(self.contact_forces), p(self.rigid_body_states)
+        b.foot_records = p(getattr(self, "foot_records", None))     # optional packed (N,4,13): replaces rigid_body_states[:, feet]
         b.height_samples = p(self.height_samples)
         b.height_min3 = p(self._height_min3)
         b.height_min3f = p(self._height_min3f)
@@ -351,6 +352,7 @@ class FusedLeggedRobot:
         if ev is not None:
             ev()
         bufs.flags |= 1          # HL_BUF_HISTORY_CLIPPED: the step just clipped the whole obs_buf (LR:168)
+        bufs.resample_host, bufs.resample_interval = None, 0      # (set per step by post_physics_step_device)
         if self.single_launch:
             return               # ids, count and terminal rows came out of the same launch
         L.check(L.lib.hl_select_and_terminal(c, b, L.ptr(self._noise.get("term45")), L.ptr(self._noise.get("term187")),
@@ -388,6 +390,7 @@ class FusedLeggedRobot:
             self.init_done = True
         self._reset_uniforms = None           # parity mode: (N, RESET_NU) pre-drawn U[0,1)
         self._episode_means = z(max(self._episode_sums_buf.shape[0], 1))
+        self._means_ws = z(self._episode_sums_buf.shape[0] + 1, dtype=torch.float64)      # zeroed once; the kernel re-arms it
         self.push_interval = int(math.ceil(self.cfg_hot.push_interval_s / self.dt))     # LR:1263
         self.resample_interval = int(self.cfg_hot.resampling_time / self.dt)            # LR:612
         self.max_episode_length_s = self.cfg_hot.episode_length_s
@@ -533,12 +536,15 @@ class FusedLeggedRobot:
             cr["lin_vel_y"][0] = float(np.clip(cr["lin_vel_y"][0] - 0.1, -getattr(R, "max_lat_curriculum", 1.0), 0.))
             cr["lin_vel_y"][1] = float(np.clip(cr["lin_vel_y"][1] + 0.1, 0., getattr(R, "max_lat_curriculum", 1.0)))
 
-    def _pre_step_callbacks(self):
+    def _pre_step_callbacks(self, resample_in_fused=False):
         """The RNG-driven part of _post_physics_step_callback that precedes the fused step (LR:612-613,631-632):
         commands of the envs whose incremented episode length hits the resampling interval (in-kernel, Philox
-        stream 2 or the parity uniforms), then the interval disturbance."""
+        stream 2 or the parity uniforms; `resample_in_fused`: the fused kernel does it itself), then the interval
+        disturbance."""
         R = self.cfg_hot.reset
-        if self.resample_interval > 0 and type(self)._resample_commands is FusedLeggedRobot._resample_commands:
+        if resample_in_fused:
+            pass
+        elif self.resample_interval > 0 and type(self)._resample_commands is FusedLeggedRobot._resample_commands:
             r = self._reset_struct(L.RESET_COMMANDS)
             L.check(L.lib.hl_resample_commands(ctypes.byref(self._c), ctypes.byref(self._buffers()), ctypes.byref(r), None, None,
                                                self.resample_interval, self.num_envs, L.stream()))
@@ -548,11 +554,13 @@ class FusedLeggedRobot:
         if R.disturbance and self.common_step_counter % self.cfg_hot.disturbance_interval == 0:
             self._disturbance_robots()
 
-    def _log_episode(self, env_ids=None):
-        """extras of reset_idx (LR:344-359); the masked means come from one launch over the device id list."""
-        L.check(L.lib.hl_episode_means(L.ptr(self._episode_sums_buf), L.ptr(self.episode_length_buf), L.ptr(self._reset_ids),
-                                       L.ptr(self._n_reset), self._episode_sums_buf.shape[0], self.num_envs, float(self.dt), 1,
-                                       L.ptr(self._episode_means), L.stream()))
+    def _log_episode(self, in_kernel=False):
+        """extras of reset_idx (LR:344-359); the masked means come from the reset launch itself (`in_kernel`) or from
+        one launch over the device id list."""
+        if not in_kernel:
+            L.check(L.lib.hl_episode_means(L.ptr(self._episode_sums_buf), L.ptr(self.episode_length_buf), L.ptr(self._reset_ids),
+                                           L.ptr(self._n_reset), self._episode_sums_buf.shape[0], self.num_envs, float(self.dt), 1,
+                                           L.ptr(self._episode_means), L.stream()))
         ep = self.extras.setdefault("episode", {})
         for k, key in enumerate(self.episode_sums.keys()):
             ep["rew_" + key] = self._episode_means[k]
@@ -577,7 +585,18 @@ class FusedLeggedRobot:
         self._philox_bias = -1                                # noise streams stay keyed by the step index 0, 1, 2, ...
         try:
             push_now = R.push_robots and self.push_interval > 0 and self.common_step_counter % self.push_interval == 0
-            self._pre_step_callbacks()
+            # the default callbacks: the fused kernel resamples the commands on the mark itself (one launch less)
+            own_cb = type(self)._pre_step_callbacks is FusedLeggedRobot._pre_step_callbacks
+            in_fused = (own_cb and not push_now and self.resample_interval > 0
+                        and type(self)._resample_commands is FusedLeggedRobot._resample_commands)
+            self._resample_struct = self._reset_struct(L.RESET_COMMANDS) if in_fused else None
+            bufs = self._buffers()
+            bufs.resample_host = ctypes.cast(ctypes.pointer(self._resample_struct), ctypes.c_void_p) if in_fused else None
+            bufs.resample_interval = self.resample_interval if in_fused else 0
+            if own_cb:
+                self._pre_step_callbacks(resample_in_fused=in_fused)
+            else:
+                self._pre_step_callbacks()
             if push_now:
                 # LR:627-628: the push changes root_states[:, 7:9] AFTER base_lin_vel was taken and BEFORE rewards /
                 # observations: the staged path splits the step around it (1 step in push_interval)
@@ -594,8 +613,9 @@ class FusedLeggedRobot:
             if self._kernel_reset_ok():
                 if R.commands_curriculum and self.common_step_counter % self.max_episode_length == 0:   # LR:306-307 (1 step in 1000)
                     self.update_command_curriculum(self._reset_ids[:int(self._n_reset.item())])
-                self._log_episode()
+                self._log_episode(in_kernel=True)
                 r = self._reset_struct()
+                r.means_out, r.means_ws = L.ptr(self._episode_means), L.ptr(self._means_ws)
                 c, b = ctypes.byref(self._c), ctypes.byref(self._buffers())
                 if push_now:
                     L.check(L.lib.hl_reset_idx(c, b, ctypes.byref(r), L.ptr(self._reset_ids), L.ptr(self._n_reset), self.num_envs, L.stream()))

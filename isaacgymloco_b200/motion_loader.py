@@ -205,6 +205,64 @@ class AMPLoader:
                                          L.ptr(out), L.ptr(lo), L.ptr(hi), b, L.stream()))
         return (out, lo, hi) if return_indices else out
 
+    # ------------------------------------------------------------------ scalar API (ML:196-204,221-229,257-267,270-313)
+    # One frame at a time: kept for API parity (the hot path is the batch form above).  A 1-sample launch of the
+    # batch kernel gives the lerp columns; get_full_frame_at_time's rotation is the reference's scalar route,
+    # `pybullet_utils.transformations.quaternion_slerp` + standardize_quaternion (ML:300-303) -- pybullet_utils is a
+    # third-party module absent from the reference tree: its published algorithm (C. Gohlke's transformations.py) is
+    # restated below on the host => parity unpinned at that one call.
+    def get_frame_at_time(self, traj_idx, time):
+        """ML:196-204 -> (42,): lerp of the AMP columns 7:49 of the two bracketing frames."""
+        return self.get_full_frame_at_time_batch(np.array([traj_idx]), np.array([float(time)]))[0, self.ROOT_ROT_END_IDX:]
+
+    @staticmethod
+    def _quaternion_slerp_host(q0, q1, fraction):
+        eps = np.finfo(float).eps * 4.0
+        q0 = np.array(q0[:4], dtype=np.float64)
+        q1 = np.array(q1[:4], dtype=np.float64)
+        q0 /= np.linalg.norm(q0)
+        q1 /= np.linalg.norm(q1)
+        if fraction == 0.0:
+            return q0
+        if fraction == 1.0:
+            return q1
+        d = float(np.dot(q0, q1))
+        if abs(abs(d) - 1.0) < eps:
+            return q0
+        if d < 0.0:
+            d, q1 = -d, -q1
+        angle = np.arccos(d)
+        if abs(angle) < eps:
+            return q0
+        isin = 1.0 / np.sin(angle)
+        return q0 * (np.sin((1.0 - fraction) * angle) * isin) + q1 * (np.sin(fraction * angle) * isin)
+
+    def blend_frame_pose(self, frame0, frame1, blend):
+        """ML:270-313 -> (49,)."""
+        q = self._quaternion_slerp_host(frame0[3:7].cpu().numpy(), frame1[3:7].cpu().numpy(), blend)
+        if q[3] < 0:                                     # motion_util.standardize_quaternion
+            q = -q
+        out = self.slerp(frame0, frame1, blend).clone()
+        out[3:7] = torch.tensor(q, dtype=torch.float32, device=self.device)
+        return out
+
+    def get_full_frame_at_time(self, traj_idx, time):
+        """ML:221-229 -> (49,)."""
+        p = float(time) / self.trajectory_lens[traj_idx]
+        n = self.trajectories_full[traj_idx].shape[0]
+        lo, hi = int(np.floor(p * n)), int(np.ceil(p * n))
+        return self.blend_frame_pose(self.trajectories_full[traj_idx][lo], self.trajectories_full[traj_idx][hi], p * n - lo)
+
+    def get_frame(self):
+        """ML:257-261: a random 42-wide AMP frame."""
+        traj_idx = self.weighted_traj_idx_sample()
+        return self.get_frame_at_time(traj_idx, self.traj_time_sample(traj_idx))
+
+    def get_full_frame(self):
+        """ML:263-267: a random full frame."""
+        traj_idx = self.weighted_traj_idx_sample()
+        return self.get_full_frame_at_time(traj_idx, self.traj_time_sample(traj_idx))
+
     def get_full_frame_batch(self, num_frames):
         if self.preload_transitions:
             idxs = np.random.choice(self.preloaded_s.shape[0], size=num_frames)
@@ -230,11 +288,12 @@ class AMPLoader:
                 idxs = np.random.choice(self.preloaded_s.shape[0], size=mini_batch_size)
                 yield self.gather_pairs(idxs)
             else:
+                # ML:331-343: a Python loop of get_frame_at_time + vstack there -- (mini_batch_size, 42) lerp frames
+                # (the 42 AMP columns 7:49, not the 30 of the preload branch); here two batch launches
                 traj_idxs = self.weighted_traj_idx_sample_batch(mini_batch_size)
                 times = self.traj_time_sample_batch(traj_idxs)
-                pick = lambda fr: torch.cat([fr[:, 7:19], fr[:, 31:49]], dim=-1)
-                yield (pick(self.get_full_frame_at_time_batch(traj_idxs, times)),
-                       pick(self.get_full_frame_at_time_batch(traj_idxs, times + self.time_between_frames)))
+                yield (self.get_full_frame_at_time_batch(traj_idxs, times)[:, self.ROOT_ROT_END_IDX:],
+                       self.get_full_frame_at_time_batch(traj_idxs, times + self.time_between_frames)[:, self.ROOT_ROT_END_IDX:])
 
     @property
     def observation_dim(self):

@@ -2,7 +2,8 @@
 
 Reference: rsl_rl/rsl_rl/storage/him_rollout_storage.py:36-177 (`HIMRolloutStorage`); the
 `compute_returns` body is byte-identical in amp_rollout_storage.py:141-155 (`RolloutStorage`), so
-`RolloutStorage` is exported as an alias.  Same constructor, field names, shapes and dtypes
+that method serves both; the AMP `RolloutStorage` class itself (history / wm_feature buffers, recurrent
+minibatches) is not part of the path and is not provided.  Same constructor, field names, shapes and dtypes
 (time-major (T,N,.) buffers, uint8 dones); `compute_returns(last_values, gamma, lam)` has the same
 signature and side effects (fills `returns`, rebinds `advantages`).
 """
@@ -244,5 +245,3 @@ class HIMRolloutStorage:
             for i in range(num_mini_batches):
                 yield self.gather_batch(indices[i * mb:(i + 1) * mb], fields)
 
-
-RolloutStorage = HIMRolloutStorage

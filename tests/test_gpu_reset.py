@@ -289,3 +289,28 @@ def test_post_physics_step_device_is_graph_capturable():
     for k in sa:
         assert torch.equal(sa[k], sb[k]), k
     assert torch.equal(a.root_states, b.root_states) and int(a._n_reset.item()) == int(b._n_reset.item()) > 0
+
+
+def test_packed_foot_records_equal_rigid_body_states():
+    """HlEnvBuffers.foot_records (N,4,13), the input a PCIe-fed host should ship, gives the same step as reading
+    rigid_body_states[:, feet_indices] (LR:203-204) -- fused kernel, fix-up and the staged methods."""
+    from gpu_helpers import make_env
+    from isaacgymloco_b200 import _lib as L
+    from isaacgymloco_b200 import config as C, synthetic as S
+    n = 4096 + 4
+    cfg = C.aliengo("stairs", num_envs=n)
+    hf = S.make_terrain(cfg, seed=4)
+    state = S.make_state(cfg, n, hf, seed=17)
+    a, b = make_env(cfg, state, hf), make_env(cfg, state, hf)
+    b.foot_records = b.rigid_body_states.view(n, cfg.num_bodies, 13)[:, cfg.feet_indices, :].contiguous()
+    b.rigid_body_states = torch.full_like(b.rigid_body_states, float("nan"))     # must not be read any more
+    b.refresh_buffers()
+    for e in (a, b):
+        e.fused_pre_reset()
+        e.fused_post_reset(with_reset_zero=True)
+    sa, sb = a.snapshot(), b.snapshot()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    for e in (a, b):
+        e._stages(L.ST_FRAME | L.ST_CONTACTS | L.ST_REWARD)
+    assert torch.equal(a.rew_buf, b.rew_buf) and torch.equal(a.feet_pos, b.feet_pos)
