@@ -309,6 +309,10 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     affinity = bind_to_gpu_numa(local)           # before any pinned allocation: H2D/D2H staging stays on the GPU's socket
+    if world > 1:
+        # env kernels on a high-priority stream: the (persistent, few-CTA) NCCL kernels of the side stream get the SM
+        # slots the env grid leaves, not the other way round
+        torch.cuda.set_stream(torch.cuda.Stream(device=device, priority=-1))
     wl = Workload(args.envs, args.rollout, rank, world, device)
     bytes_tab = R.per_env_step_bytes(wl.cfg, args.rollout)
 
@@ -319,9 +323,8 @@ def run_gpu_arm(args):
     # (hybrid_ppo.py:279-281).  The 3-double advantage moments ride inside the rollout (storage.normalize_advantages).
     comm_stream = torch.cuda.Stream() if world > 1 and not args.no_comm else None
     if comm_stream is not None:
-        grads = torch.randn(AC_PARAMS, device=device)
+        grads = torch.randn(AC_PARAMS + 1, device=device)      # + the adaptive-KL scalar: needed by the same optimiser step, same message
         est_grads = torch.randn(EST_PARAMS, device=device)
-        kl = torch.zeros(1, device=device)
         disc_grads = torch.randn(DISC_PARAMS, device=device) if args.amp else None
         norm_stats = torch.zeros(61, dtype=torch.float64, device=device) if args.amp else None
 
@@ -329,7 +332,6 @@ def run_gpu_arm(args):
         for _ in range(20):
             dist.all_reduce(est_grads, op=dist.ReduceOp.AVG)
             dist.all_reduce(grads, op=dist.ReduceOp.AVG)
-            dist.all_reduce(kl, op=dist.ReduceOp.AVG)
             if args.amp:
                 dist.all_reduce(disc_grads, op=dist.ReduceOp.AVG)
                 dist.all_reduce(norm_stats, op=dist.ReduceOp.SUM)
@@ -422,7 +424,7 @@ def run_gpu_arm(args):
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
         "gpu_launches": launches, "roofline": roofline, "timing_mode": mode, "cpu_affinity": affinity,
         "exchange": None if world == 1 else ("off (--no-comm)" if args.no_comm else
-                                             "20 x {estimator 59,875 + actor-critic 545,660 fp32 grads + KL scalar}" +
+                                             "20 x {estimator 59,875 fp32; actor-critic 545,660 fp32 grads + KL scalar (one message)}" +
                                              (" + {discriminator 587,777 fp32 + 61-double normaliser}" if args.amp else "") +
                                              " all-reduces per rollout on a side stream; 3-double advantage moments inside the rollout"),
         "direct_launch": {"value": world * args.envs * args.rollout * args.steps / (ms_direct * 1e-3), "unit": UNIT,

@@ -241,6 +241,13 @@ int hl_select_and_terminal(const HlCfg* cfg, const HlEnvBuffers* bufs, const flo
                            float* term_priv_obs_out, float* term_amp_out, void* workspace, int64_t n_envs,
                            void* stream);
 
+/* hl_select_and_terminal + hl_reset_and_fixup in ONE launch (LR:225-241 for the envs that reset): ids, count and terminal
+ * rows as above; the warp that wrote an env's terminal rows then re-draws its state, zeroes its buffers, accumulates the
+ * episode-logging means (reset->means_out / means_ws) and redoes its scan, observation slot 0 and roll. */
+int hl_select_terminal_reset(const HlCfg* cfg, const HlEnvBuffers* bufs, const HlReset* reset, const float* term_noise_u45,
+                             const float* term_noise_u187, int64_t* ids_out, int32_t* count_out, float* term_priv_obs_out,
+                             float* term_amp_out, void* workspace, int64_t n_envs, void* stream);
+
 /* After reset_idx mutated the reset envs: re-scan their heights (LR:332-333), rewrite slot 0 of
  * obs_buf and privileged_obs_buf from the post-reset state (stale base velocities, LR:232) and
  * redo the end-of-step roll for them (LR:235-241).  with_reset_zero != 0 first applies the

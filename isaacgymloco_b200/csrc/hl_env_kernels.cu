@@ -521,6 +521,231 @@ __device__ __forceinline__ void hl_reset_draw_env(const HlCfg& c, const HlEnvBuf
   __syncwarp();
 }
 
+// One env through any subset of the stages, by one warp (or, with a split, by one warp of its group: `lead` does the
+// buffer resets, slot 0 / privileged_obs[0:51] and the roll, the others the height iterations it % it_mod == it_rem).
+// `items`: length of the id list -- the warp that completes it finalises the episode-logging means; < 0 = the caller
+// finalises them itself.  `st`: this warp's staging area (hl_warp_stage_floats floats of shared memory).
+__device__ __forceinline__ void hl_stage_one(const HlCfg& c, const HlEnvBuffers& b, const HlReset& rs, const unsigned stages, float* st,
+                                             const long long e, const long long n, const long long items, const int lane,
+                                             const bool lead, const bool scans, const int it_mod, const int it_rem) {
+  const int B = c.num_bodies;
+  const int P = c.n_px * c.n_py;
+  const int PD = hl_priv_dim(c);
+  __syncwarp();   // the previous env's staged records are no longer read
+  if ((stages & HL_ST_RESET_DRAW) && lead) hl_reset_draw_env(c, b, rs, e, lane);   // writes the env's root / dof / command rows
+  EnvView v;
+  hl_stage_env(st, c, b, e, lane, (stages & HL_ST_RESET_ZERO) != 0, v);
+  if ((stages & HL_ST_RESET_ZERO) && lead) {  // LR:323-329,350,361
+    if (lane < 12) {
+      b.last_actions[e * 12 + lane] = 0.0f;
+      b.last_last_actions[e * 12 + lane] = 0.0f;
+      b.last_dof_pos[e * 12 + lane] = 0.0f;
+      b.last_dof_vel[e * 12 + lane] = 0.0f;
+      b.last_torques[e * 12 + lane] = 0.0f;
+    }
+    if (lane < 4) b.feet_air_time[e * 4 + lane] = 0.0f;
+    if (b.episode_sums) {
+      if ((stages & HL_ST_RESET_DRAW) && rs.means_out && rs.means_ws) {   // LR:346-350: the logged means, before the rows are zeroed
+        const long long len = b.episode_length_buf[e] < 1 ? 1 : b.episode_length_buf[e];
+        for (int k = lane; k < c.n_terms + c.has_termination_term; k += 32)
+          atomicAdd(rs.means_ws + k, (double)__fdiv_rn(__fdiv_rn(b.episode_sums[(long long)k * n + e], (float)len), c.dt));
+        // the warp that completes the list turns the sums into means and re-arms the workspace (graph safe)
+        const int R = c.n_terms + c.has_termination_term;
+        __threadfence();
+        __syncwarp();
+        unsigned long long done = 0;
+        if (lane == 0 && items >= 0) done = atomicAdd(reinterpret_cast<unsigned long long*>(rs.means_ws + R), 1ull) + 1ull;
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (items >= 0 && done == (unsigned long long)items) {
+          __threadfence();
+          for (int k = lane; k < R; k += 32) {
+            const double t = *reinterpret_cast<volatile double*>(rs.means_ws + k);
+            rs.means_out[k] = (float)(t / (double)items);
+            rs.means_ws[k] = 0.0;
+          }
+          if (lane == 0) *reinterpret_cast<unsigned long long*>(rs.means_ws + R) = 0ull;
+        }
+      }
+      for (int k = lane; k < c.n_terms + c.has_termination_term; k += 32) b.episode_sums[(long long)k * n + e] = 0.0f;
+    }
+    if (lane == 0) {
+      b.episode_length_buf[e] = 0;
+      b.reset_buf[e] = 1;
+    }
+    __syncwarp();
+  }
+  EnvScalars s;
+  s.gid = e + c.env_id_offset;
+  s.feet_shift = 0;
+  s.base_h = 0.0f;
+  s.terrain_level = b.terrain_levels ? b.terrain_levels[e] : 0;
+  s.ep_len = b.episode_length_buf[e];
+  for (int k = 0; k < 4; ++k) s.cmd[k] = b.commands[e * 4 + k];
+  for (int k = 0; k < 4; ++k) s.air[k] = b.feet_air_time[e * 4 + k];
+  unsigned last = 0, filt = 0;
+  for (int f = 0; f < 4; ++f) {
+    last |= (b.last_contacts[e * 4 + f] ? 1u : 0u) << f;
+    filt |= (b.contact_filt[e * 4 + f] ? 1u : 0u) << f;
+  }
+  s.last_contact = last;
+  s.cfilt = filt;
+  s.contact = 0;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) s.contact |= (v.cf[c.feet_idx[f] * 3 + 2] > 1.0f ? 1u : 0u) << f;
+  s.reset = b.reset_buf[e] != 0;
+  s.time_out = b.time_out_buf[e] != 0;
+  __syncwarp();
+
+  if (!lead) goto heights_only;   // (parts > 1) the other warps of the env: height iterations only
+  if (stages & HL_ST_COUNTERS) {
+    s.ep_len += 1;
+    if (lane == 0) b.episode_length_buf[e] = s.ep_len;
+  }
+  if (stages & HL_ST_FRAME) {
+    hl_frame(v, s);
+    if (lane < 3) {
+      b.base_lin_vel[e * 3 + lane] = s.blv[lane];
+      b.base_ang_vel[e * 3 + lane] = s.bav[lane];
+      b.projected_gravity[e * 3 + lane] = s.pg[lane];
+    }
+  } else {
+    for (int k = 0; k < 3; ++k) {
+      s.blv[k] = b.base_lin_vel[e * 3 + k];
+      s.bav[k] = b.base_ang_vel[e * 3 + k];
+      s.pg[k] = b.projected_gravity[e * 3 + k];
+    }
+  }
+  if (stages & HL_ST_CONTACTS) {
+    hl_contacts(c, v, last, s);
+    if (lane < 4) {
+      b.contact_filt[e * 4 + lane] = (s.cfilt >> lane) & 1u;
+      b.last_contacts[e * 4 + lane] = (s.last_contact >> lane) & 1u;
+    }
+    if (lane < 12) {
+      const int f = lane / 3, k = lane % 3;
+      if (b.feet_pos) b.feet_pos[e * 12 + lane] = v.fpos[f][k];
+      if (b.feet_vel) b.feet_vel[e * 12 + lane] = v.fvel[f][k];
+    }
+  }
+  if ((stages & HL_ST_HEADING) && c.heading_command) {
+    s.cmd[2] = hl_heading_command(v.root + 3, s.cmd[3]);
+    if (lane == 0) b.commands[e * 4 + 2] = s.cmd[2];
+  }
+heights_only:
+  float myh[8];
+  const bool do_h = (stages & HL_ST_HEIGHTS) && c.measure_heights && scans;
+  const bool want_base = ((stages & HL_ST_REWARD) && hl_needs_base_height(c)) || (stages & HL_ST_BASE_HEIGHT);
+  if (do_h || want_base) {
+    ScanOut o;
+    o.measured = b.measured_heights + e * P;
+    o.priv_heights = nullptr;
+    o.idx = b.height_idx_out ? b.height_idx_out + e * P * 2 : nullptr;
+    o.u187 = nullptr;
+    o.clip = false;
+    o.keep = myh;
+    s.base_h = hl_warp_scan_env(c, b, v.root, (unsigned long long)s.gid, lane, do_h, want_base && lead, o, 0u, it_mod, it_rem);
+    if ((stages & HL_ST_BASE_HEIGHT) && b.base_height_out && lane == 0) b.base_height_out[e] = s.base_h;
+  }
+  if ((stages & HL_ST_TERMINATION) && lead) {
+    hl_check_termination(c, v, s);
+    if (lane == 0) {
+      b.reset_buf[e] = s.reset;
+      b.time_out_buf[e] = s.time_out;
+    }
+  }
+  if ((stages & HL_ST_REWARD) && lead) {
+    const float rew = hl_compute_reward(c, b, v, s, b.episode_sums ? b.episode_sums + e : nullptr, n, lane == 0);
+    if (lane == 0) b.rew_buf[e] = rew;
+    if (lane < 4) {
+      b.feet_air_time[e * 4 + lane] = s.air[lane];
+      b.last_contacts[e * 4 + lane] = (s.last_contact >> lane) & 1u;
+    }
+  }
+  if (stages & HL_ST_OBS) {
+    const bool clip = stages & HL_ST_OBS_CLIP;
+    const float cl = c.clip_obs;
+    // history first (registers), then the new slot: safe when obs_buf_out aliases obs_buf_in
+    float old[8];
+    if (!(stages & HL_ST_OBS_NOSHIFT) && lead) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = i * 32 + lane;
+        old[i] = k < 225 ? b.obs_buf_in[e * 270 + k] : 0.0f;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = i * 32 + lane;
+        if (k < 225) b.obs_buf_out[e * 270 + 45 + k] = clip ? hl_clampf(old[i], -cl, cl) : old[i];
+      }
+    }
+    if (lead) {
+      uint4 nb = make_uint4(0u, 0u, 0u, 0u);
+      int cb, c0;
+      hl_cur_noise_slot(P, cb, c0);
+      if (c.add_noise && !b.noise_u45)
+        nb = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)s.gid, (unsigned)(cb * 32 + lane), 0u);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        if (k < 45) {
+          float u = 0.5f;
+          if (c.add_noise) u = b.noise_u45 ? b.noise_u45[e * 45 + k] : hl_u01(hl_pick(nb, c0 + h));
+          float x = hl_add_noise45(c, hl_obs45(c, v, s, k), u, k);
+          if (clip) x = hl_clampf(x, -cl, cl);
+          b.obs_buf_out[e * 270 + k] = x;
+          b.privileged_obs_buf[e * PD + k] = x;
+        }
+      }
+    }
+    if (lane < 6 && lead) {
+      float x = lane < 3 ? s.blv[lane] * c.obs_lin_vel : b.disturbance[e * B * 3 + (lane - 3)];
+      if (clip) x = hl_clampf(x, -cl, cl);
+      b.privileged_obs_buf[e * PD + 45 + lane] = x;
+    }
+    if (c.measure_heights && scans) {
+      HeightNoise hn;
+      const float rz = v.root[2];
+      int pass = -1;
+      for (int it = 0; it * 32 < P; ++it) {
+        if ((it % it_mod) != it_rem) continue;
+        const int p = it * 32 + lane;
+        if (!b.noise_u187 && (it >> 2) != pass) { pass = it >> 2; hn.refill(b, (unsigned long long)s.gid, pass, lane, 0u); }
+        float u = 0.5f;
+        if (c.add_noise) u = b.noise_u187 ? (p < P ? b.noise_u187[e * P + p] : 0.5f) : hn.get(it, lane);
+        if (p < P) {
+          const float mh = do_h ? myh[it] : b.measured_heights[e * P + p];
+          float hv = hl_obs_height(c, rz, mh, u);
+          if (clip) hv = hl_clampf(hv, -cl, cl);
+          b.privileged_obs_buf[e * PD + 51 + p] = hv;
+        }
+      }
+    }
+  }
+  if ((stages & HL_ST_ROLL) && lead) {  // LR:235-241 (reads complete before writes: llact <- lact <- act)
+    __syncwarp();
+    float la = 0.f, a = 0.f, dp = 0.f, dv = 0.f, tq = 0.f, rv = 0.f;
+    if (lane < 12) {
+      la = v.lact[lane];
+      a = v.act[lane];
+      dp = v.dof_pos(lane);
+      dv = v.dof_vel(lane);
+      tq = v.tq[lane];
+    }
+    if (lane < 6) rv = v.root[7 + lane];
+    __syncwarp();
+    if (lane < 12) {
+      b.last_last_actions[e * 12 + lane] = la;
+      b.last_actions[e * 12 + lane] = a;
+      b.last_dof_pos[e * 12 + lane] = dp;
+      b.last_dof_vel[e * 12 + lane] = dv;
+      b.last_torques[e * 12 + lane] = tq;
+    }
+    if (lane < 6) b.last_root_vel[e * 6 + lane] = rv;
+    if (lane < 3) b.disturbance[e * B * 3 + lane] = 0.0f;
+  }
+}
+
 template <unsigned STAGES, bool SPLIT = false>  // STAGES 0 = take the mask at run time; otherwise everything else is compiled out
 __global__ void __launch_bounds__(256, 3) hl_stage_kernel(HlCfg c, HlEnvBuffers b, unsigned stages_rt,
                                                        const long long* __restrict__ ids,
@@ -535,11 +760,8 @@ __global__ void __launch_bounds__(256, 3) hl_stage_kernel(HlCfg c, HlEnvBuffers 
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long items = ids ? (long long)*n_ids : n;
-  const int B = c.num_bodies;
-  const int P = c.n_px * c.n_py;
-  const int PD = hl_priv_dim(c);
   extern __shared__ __align__(16) float stage_smem[];
-  float* st = stage_smem + (threadIdx.x >> 5) * hl_warp_stage_floats(B);
+  float* st = stage_smem + (threadIdx.x >> 5) * hl_warp_stage_floats(c.num_bodies);
   const int np = (SPLIT && parts > 1) ? parts : 1;   // !SPLIT: folds to the one-warp-per-env code
   for (long long w = warp0; w < items * np; w += nwarps) {
     const long long it0 = w / np;
@@ -549,219 +771,7 @@ __global__ void __launch_bounds__(256, 3) hl_stage_kernel(HlCfg c, HlEnvBuffers 
     const int it_mod = np == 1 ? 1 : np - 1, it_rem = np == 1 ? 0 : part - 1;
     const long long e = ids ? ids[it0] : it0;
     if (e < 0 || e >= n) continue;
-    __syncwarp();   // the previous env's staged records are no longer read
-    if ((stages & HL_ST_RESET_DRAW) && lead) hl_reset_draw_env(c, b, rs, e, lane);   // writes the env's root / dof / command rows
-    EnvView v;
-    hl_stage_env(st, c, b, e, lane, (stages & HL_ST_RESET_ZERO) != 0, v);
-    if ((stages & HL_ST_RESET_ZERO) && lead) {  // LR:323-329,350,361
-      if (lane < 12) {
-        b.last_actions[e * 12 + lane] = 0.0f;
-        b.last_last_actions[e * 12 + lane] = 0.0f;
-        b.last_dof_pos[e * 12 + lane] = 0.0f;
-        b.last_dof_vel[e * 12 + lane] = 0.0f;
-        b.last_torques[e * 12 + lane] = 0.0f;
-      }
-      if (lane < 4) b.feet_air_time[e * 4 + lane] = 0.0f;
-      if (b.episode_sums) {
-        if ((stages & HL_ST_RESET_DRAW) && rs.means_out && rs.means_ws) {   // LR:346-350: the logged means, before the rows are zeroed
-          const long long len = b.episode_length_buf[e] < 1 ? 1 : b.episode_length_buf[e];
-          for (int k = lane; k < c.n_terms + c.has_termination_term; k += 32)
-            atomicAdd(rs.means_ws + k, (double)__fdiv_rn(__fdiv_rn(b.episode_sums[(long long)k * n + e], (float)len), c.dt));
-          // the warp that completes the list turns the sums into means and re-arms the workspace (graph safe)
-          const int R = c.n_terms + c.has_termination_term;
-          __threadfence();
-          __syncwarp();
-          unsigned long long done = 0;
-          if (lane == 0) done = atomicAdd(reinterpret_cast<unsigned long long*>(rs.means_ws + R), 1ull) + 1ull;
-          done = __shfl_sync(0xffffffffu, done, 0);
-          if (done == (unsigned long long)items) {
-            __threadfence();
-            for (int k = lane; k < R; k += 32) {
-              const double t = *reinterpret_cast<volatile double*>(rs.means_ws + k);
-              rs.means_out[k] = (float)(t / (double)items);
-              rs.means_ws[k] = 0.0;
-            }
-            if (lane == 0) *reinterpret_cast<unsigned long long*>(rs.means_ws + R) = 0ull;
-          }
-        }
-        for (int k = lane; k < c.n_terms + c.has_termination_term; k += 32) b.episode_sums[(long long)k * n + e] = 0.0f;
-      }
-      if (lane == 0) {
-        b.episode_length_buf[e] = 0;
-        b.reset_buf[e] = 1;
-      }
-      __syncwarp();
-    }
-    EnvScalars s;
-    s.gid = e + c.env_id_offset;
-    s.feet_shift = 0;
-    s.base_h = 0.0f;
-    s.terrain_level = b.terrain_levels ? b.terrain_levels[e] : 0;
-    s.ep_len = b.episode_length_buf[e];
-    for (int k = 0; k < 4; ++k) s.cmd[k] = b.commands[e * 4 + k];
-    for (int k = 0; k < 4; ++k) s.air[k] = b.feet_air_time[e * 4 + k];
-    unsigned last = 0, filt = 0;
-    for (int f = 0; f < 4; ++f) {
-      last |= (b.last_contacts[e * 4 + f] ? 1u : 0u) << f;
-      filt |= (b.contact_filt[e * 4 + f] ? 1u : 0u) << f;
-    }
-    s.last_contact = last;
-    s.cfilt = filt;
-    s.contact = 0;
-#pragma unroll
-    for (int f = 0; f < 4; ++f) s.contact |= (v.cf[c.feet_idx[f] * 3 + 2] > 1.0f ? 1u : 0u) << f;
-    s.reset = b.reset_buf[e] != 0;
-    s.time_out = b.time_out_buf[e] != 0;
-    __syncwarp();
-
-    if (!lead) goto heights_only;   // (parts > 1) the other warps of the env: height iterations only
-    if (stages & HL_ST_COUNTERS) {
-      s.ep_len += 1;
-      if (lane == 0) b.episode_length_buf[e] = s.ep_len;
-    }
-    if (stages & HL_ST_FRAME) {
-      hl_frame(v, s);
-      if (lane < 3) {
-        b.base_lin_vel[e * 3 + lane] = s.blv[lane];
-        b.base_ang_vel[e * 3 + lane] = s.bav[lane];
-        b.projected_gravity[e * 3 + lane] = s.pg[lane];
-      }
-    } else {
-      for (int k = 0; k < 3; ++k) {
-        s.blv[k] = b.base_lin_vel[e * 3 + k];
-        s.bav[k] = b.base_ang_vel[e * 3 + k];
-        s.pg[k] = b.projected_gravity[e * 3 + k];
-      }
-    }
-    if (stages & HL_ST_CONTACTS) {
-      hl_contacts(c, v, last, s);
-      if (lane < 4) {
-        b.contact_filt[e * 4 + lane] = (s.cfilt >> lane) & 1u;
-        b.last_contacts[e * 4 + lane] = (s.last_contact >> lane) & 1u;
-      }
-      if (lane < 12) {
-        const int f = lane / 3, k = lane % 3;
-        if (b.feet_pos) b.feet_pos[e * 12 + lane] = v.fpos[f][k];
-        if (b.feet_vel) b.feet_vel[e * 12 + lane] = v.fvel[f][k];
-      }
-    }
-    if ((stages & HL_ST_HEADING) && c.heading_command) {
-      s.cmd[2] = hl_heading_command(v.root + 3, s.cmd[3]);
-      if (lane == 0) b.commands[e * 4 + 2] = s.cmd[2];
-    }
-  heights_only:
-    float myh[8];
-    const bool do_h = (stages & HL_ST_HEIGHTS) && c.measure_heights && scans;
-    const bool want_base = ((stages & HL_ST_REWARD) && hl_needs_base_height(c)) || (stages & HL_ST_BASE_HEIGHT);
-    if (do_h || want_base) {
-      ScanOut o;
-      o.measured = b.measured_heights + e * P;
-      o.priv_heights = nullptr;
-      o.idx = b.height_idx_out ? b.height_idx_out + e * P * 2 : nullptr;
-      o.u187 = nullptr;
-      o.clip = false;
-      o.keep = myh;
-      s.base_h = hl_warp_scan_env(c, b, v.root, (unsigned long long)s.gid, lane, do_h, want_base && lead, o, 0u, it_mod, it_rem);
-      if ((stages & HL_ST_BASE_HEIGHT) && b.base_height_out && lane == 0) b.base_height_out[e] = s.base_h;
-    }
-    if ((stages & HL_ST_TERMINATION) && lead) {
-      hl_check_termination(c, v, s);
-      if (lane == 0) {
-        b.reset_buf[e] = s.reset;
-        b.time_out_buf[e] = s.time_out;
-      }
-    }
-    if ((stages & HL_ST_REWARD) && lead) {
-      const float rew = hl_compute_reward(c, b, v, s, b.episode_sums ? b.episode_sums + e : nullptr, n, lane == 0);
-      if (lane == 0) b.rew_buf[e] = rew;
-      if (lane < 4) {
-        b.feet_air_time[e * 4 + lane] = s.air[lane];
-        b.last_contacts[e * 4 + lane] = (s.last_contact >> lane) & 1u;
-      }
-    }
-    if (stages & HL_ST_OBS) {
-      const bool clip = stages & HL_ST_OBS_CLIP;
-      const float cl = c.clip_obs;
-      // history first (registers), then the new slot: safe when obs_buf_out aliases obs_buf_in
-      float old[8];
-      if (!(stages & HL_ST_OBS_NOSHIFT) && lead) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = i * 32 + lane;
-          old[i] = k < 225 ? b.obs_buf_in[e * 270 + k] : 0.0f;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = i * 32 + lane;
-          if (k < 225) b.obs_buf_out[e * 270 + 45 + k] = clip ? hl_clampf(old[i], -cl, cl) : old[i];
-        }
-      }
-      if (lead) {
-        uint4 nb = make_uint4(0u, 0u, 0u, 0u);
-        int cb, c0;
-        hl_cur_noise_slot(P, cb, c0);
-        if (c.add_noise && !b.noise_u45)
-          nb = hl_noise_block(b.philox_seed, b.philox_offset, (unsigned long long)s.gid, (unsigned)(cb * 32 + lane), 0u);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int k = lane + 32 * h;
-          if (k < 45) {
-            float u = 0.5f;
-            if (c.add_noise) u = b.noise_u45 ? b.noise_u45[e * 45 + k] : hl_u01(hl_pick(nb, c0 + h));
-            float x = hl_add_noise45(c, hl_obs45(c, v, s, k), u, k);
-            if (clip) x = hl_clampf(x, -cl, cl);
-            b.obs_buf_out[e * 270 + k] = x;
-            b.privileged_obs_buf[e * PD + k] = x;
-          }
-        }
-      }
-      if (lane < 6 && lead) {
-        float x = lane < 3 ? s.blv[lane] * c.obs_lin_vel : b.disturbance[e * B * 3 + (lane - 3)];
-        if (clip) x = hl_clampf(x, -cl, cl);
-        b.privileged_obs_buf[e * PD + 45 + lane] = x;
-      }
-      if (c.measure_heights && scans) {
-        HeightNoise hn;
-        const float rz = v.root[2];
-        int pass = -1;
-        for (int it = 0; it * 32 < P; ++it) {
-          if ((it % it_mod) != it_rem) continue;
-          const int p = it * 32 + lane;
-          if (!b.noise_u187 && (it >> 2) != pass) { pass = it >> 2; hn.refill(b, (unsigned long long)s.gid, pass, lane, 0u); }
-          float u = 0.5f;
-          if (c.add_noise) u = b.noise_u187 ? (p < P ? b.noise_u187[e * P + p] : 0.5f) : hn.get(it, lane);
-          if (p < P) {
-            const float mh = do_h ? myh[it] : b.measured_heights[e * P + p];
-            float hv = hl_obs_height(c, rz, mh, u);
-            if (clip) hv = hl_clampf(hv, -cl, cl);
-            b.privileged_obs_buf[e * PD + 51 + p] = hv;
-          }
-        }
-      }
-    }
-    if ((stages & HL_ST_ROLL) && lead) {  // LR:235-241 (reads complete before writes: llact <- lact <- act)
-      __syncwarp();
-      float la = 0.f, a = 0.f, dp = 0.f, dv = 0.f, tq = 0.f, rv = 0.f;
-      if (lane < 12) {
-        la = v.lact[lane];
-        a = v.act[lane];
-        dp = v.dof_pos(lane);
-        dv = v.dof_vel(lane);
-        tq = v.tq[lane];
-      }
-      if (lane < 6) rv = v.root[7 + lane];
-      __syncwarp();
-      if (lane < 12) {
-        b.last_last_actions[e * 12 + lane] = la;
-        b.last_actions[e * 12 + lane] = a;
-        b.last_dof_pos[e * 12 + lane] = dp;
-        b.last_dof_vel[e * 12 + lane] = dv;
-        b.last_torques[e * 12 + lane] = tq;
-      }
-      if (lane < 6) b.last_root_vel[e * 6 + lane] = rv;
-      if (lane < 3) b.disturbance[e * B * 3 + lane] = 0.0f;
-    }
+    hl_stage_one(c, b, rs, stages, st, e, n, items, lane, lead, scans, it_mod, it_rem);
   }
 }
 
@@ -995,11 +1005,15 @@ extern "C" int hl_terminal_rows(const HlCfg* cfg, const HlEnvBuffers* bufs, cons
 // were dispatched earlier and publish right after their scan) -> ordered ids -> the CTA's warps
 // write the rows of its own reset envs.  ws = {pad, done, epoch, pad, state[nblocks]}.
 constexpr int SEL_ENVS = 256;   // small tiles: the rows of a CTA's ~6 reset envs go one per warp
+// RESET: each warp, right after the terminal rows of a reset env (pre-reset state), also runs that env's reset_idx
+// (re-draws, buffer zeroing, episode-logging sums) and post-reset fix-up (re-scan, slot 0, roll) -- LR:225-241 for the
+// reset envs in ONE launch; the last CTA to finish turns the logging sums into means.
+template <bool RESET>
 __global__ void __launch_bounds__(256) hl_select_terminal_kernel(HlCfg c, HlEnvBuffers b, const float* __restrict__ u45,
                                                                  const float* __restrict__ u187,
                                                                  long long* __restrict__ ids_out, int* __restrict__ count_out,
                                                                  float* __restrict__ out_priv, float* __restrict__ out_amp,
-                                                                 unsigned long long* ws, long long n) {
+                                                                 unsigned long long* ws, long long n, HlReset rs) {
   __shared__ int warp_tot[8];
   __shared__ int s_excl, s_total;
   __shared__ unsigned s_epoch;
@@ -1134,12 +1148,29 @@ __global__ void __launch_bounds__(256) hl_select_terminal_kernel(HlCfg c, HlEnvB
         else x = v.dof_vel(lane - 18);
         out_amp[r * 30 + lane] = x;
       }
+      if (RESET) {   // the terminal rows are out: this env may now be reset (same warp, program order)
+        extern __shared__ __align__(16) float sel_stage[];
+        __syncwarp();
+        hl_stage_one(c, b, rs, HL_ST_HEIGHTS | HL_ST_OBS | HL_ST_OBS_NOSHIFT | HL_ST_OBS_CLIP | HL_ST_ROLL | HL_ST_RESET_ZERO | HL_ST_RESET_DRAW,
+                     sel_stage + wid * hl_warp_stage_floats(c.num_bodies), e, n, -1, lane, true, true, 1, 0);
+        staged = false;
+      }
     }
   }
   __syncthreads();
   if (tid == 0) {  // last CTA re-arms the workspace (graph safe)
     __threadfence();
     if (atomicAdd(ctrl + 1, 1u) == nblocks - 1) {
+      if (RESET && rs.means_out && rs.means_ws && b.episode_sums) {   // every CTA's logging sums are in: LR:346-350 means
+        __threadfence();
+        const int total = *reinterpret_cast<volatile int*>(count_out);
+        const int R = c.n_terms + c.has_termination_term;
+        for (int k = 0; k < R; ++k) {
+          const double t = *reinterpret_cast<volatile double*>(rs.means_ws + k);
+          if (total > 0) rs.means_out[k] = (float)(t / (double)total);
+          rs.means_ws[k] = 0.0;
+        }
+      }
       ctrl[0] = 0u;
       ctrl[1] = 0u;
       ctrl[2] = s_epoch;
@@ -1155,8 +1186,25 @@ extern "C" int hl_select_and_terminal(const HlCfg* cfg, const HlEnvBuffers* bufs
   if (int r = check_cfg(cfg, bufs)) return r;
   HL_CHECK_ARG(ids_out && count_out && workspace && bufs->reset_buf, "null pointer");
   if (n <= 0) return HL_OK;
-  hl_launch(hl_select_terminal_kernel, dim3((unsigned)((n + SEL_ENVS - 1) / SEL_ENVS)), dim3(256), 0, (cudaStream_t)stream,
-            *cfg, *bufs, u45, u187, (long long*)ids_out, count_out, out_priv, out_amp, (unsigned long long*)workspace, n);
+  HlReset none = {};
+  hl_launch(hl_select_terminal_kernel<false>, dim3((unsigned)((n + SEL_ENVS - 1) / SEL_ENVS)), dim3(256), 0, (cudaStream_t)stream,
+            *cfg, *bufs, u45, u187, (long long*)ids_out, count_out, out_priv, out_amp, (unsigned long long*)workspace, n, none);
+  HL_CHECK_LAUNCH();
+  return HL_OK;
+}
+
+extern "C" int hl_select_terminal_reset(const HlCfg* cfg, const HlEnvBuffers* bufs, const HlReset* reset, const float* u45,
+                                        const float* u187, int64_t* ids_out, int32_t* count_out, float* out_priv, float* out_amp,
+                                        void* workspace, int64_t n, void* stream) {
+  if (int r = check_cfg(cfg, bufs)) return r;
+  HL_CHECK_ARG(ids_out && count_out && workspace && bufs->reset_buf && out_priv, "null pointer");
+  HL_CHECK_ARG(reset && reset->struct_bytes == (int)sizeof(HlReset), "needs a HlReset (size mismatch?)");
+  HL_CHECK_ARG(reset->root_states && reset->dof_state && reset->commands && reset->env_origins, "HlReset: null state tensor");
+  if (n <= 0) return HL_OK;
+  const size_t smem = (size_t)8 * hl_warp_stage_floats(cfg->num_bodies) * sizeof(float);
+  HL_CHECK_ARG(smem <= 40 * 1024, "num_bodies too large for the per-warp staging area");
+  hl_launch(hl_select_terminal_kernel<true>, dim3((unsigned)((n + SEL_ENVS - 1) / SEL_ENVS)), dim3(256), smem, (cudaStream_t)stream,
+            *cfg, *bufs, u45, u187, (long long*)ids_out, count_out, out_priv, out_amp, (unsigned long long*)workspace, n, *reset);
   HL_CHECK_LAUNCH();
   return HL_OK;
 }
