@@ -62,6 +62,68 @@ static inline void hl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size
 // look-back state of a CTA / tile in the ordered reset-id compaction: epoch << 32 | flag << 30 | value
 constexpr unsigned long long HL_LB_AGG = 1ull << 30, HL_LB_PREFIX = 2ull << 30, HL_LB_VALUE = (1ull << 30) - 1ull;
 
+#ifndef HL_PK_WAIT_HINT
+#define HL_PK_WAIT_HINT 0           // ns: mbarrier.try_wait suspend-time hint for long waits; 0 = probe + nanosleep
+#endif
+#ifndef HL_PK_WAIT_NS
+#define HL_PK_WAIT_NS 500           // sleep between probes of a long wait (measured: 128 -> 500 ns: -3 us per launch)
+#endif
+// ----------------------------------------------------------------------------- mbarrier / TMA (sm_90+: cp.async.bulk)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// same for the S warps' long waits: try_wait with a suspend-time hint parks the warp in hardware for up
+// to that many ns per probe instead of spinning through issue slots the H warps need
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+#if HL_PK_WAIT_HINT
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"((unsigned)HL_PK_WAIT_HINT) : "memory");
+#else
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(HL_PK_WAIT_NS);
+  }
+#endif
+}
+// 1-D TMA bulk copy global -> shared; completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void tma_load(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------- reward term ids
 // sorted() order of the 51 unique `_reward_*` names (legged_robot.py:1444-1770); mirrored by
 // isaacgymloco_b200/config.py::REWARD_TERMS.
