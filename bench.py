@@ -242,19 +242,25 @@ class Workload:
         self.env._delay_actions()
         self.fused_ms = []            # CUDA-event pairs around the dominant kernel
         self.launches = 0
+        self.exchange_cb = None       # N>1: called with the env-step index right after the fused launch is queued
 
-    def env_step(self, time_fused=False):
+    def env_step(self, time_fused=False, k_step=0):
         env = self.env
         for k in range(env.cfg_hot.decimation):
             env._compute_torques_into(env.delayed_actions[:, k], env.torques)
-        if time_fused:
+        cb = self.exchange_cb
+        if time_fused or cb is not None:
             def hook():
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
+                if time_fused:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
 
                 def after():
-                    e1.record()
-                    self.fused_ms.append((e0, e1))
+                    if time_fused:
+                        e1.record()
+                        self.fused_ms.append((e0, e1))
+                    if cb is not None:
+                        cb(k_step)
                 return after
             env._fused_event_hook = hook
         else:
@@ -265,8 +271,8 @@ class Workload:
         self.launches += env.cfg_hot.decimation + (2 if env.single_launch else 3)
 
     def rollout(self, time_fused=False, finish=True):
-        for _ in range(self.t_len):
-            self.env_step(time_fused)
+        for k in range(self.t_len):
+            self.env_step(time_fused, k)
         # compute_returns = GAE scan, [all-reduce of the 3 moments when sharded], normalisation
         self.storage.gae_scan(self.last_values, self.cfg.gamma, self.cfg.lam)
         if finish:
@@ -322,27 +328,46 @@ def run_gpu_arm(args):
     # also the discriminator gradient (hybrid_ppo.py:271, 587,777 fp32) and the 61-double normaliser merge
     # (hybrid_ppo.py:279-281).  The 3-double advantage moments ride inside the rollout (storage.normalize_advantages).
     comm_stream = torch.cuda.Stream() if world > 1 and not args.no_comm else None
+    if world > 1:
+        # the in-rollout statistics get their own communicator: collectives of one communicator execute in issue order,
+        # so on a shared one the 3-double moments would queue behind every gradient message still in flight
+        wl.storage.process_group = dist.new_group(backend="nccl")
     if comm_stream is not None:
+        grad_group = dist.new_group(backend="nccl")
         grads = torch.randn(AC_PARAMS + 1, device=device)      # + the adaptive-KL scalar: needed by the same optimiser step, same message
         est_grads = torch.randn(EST_PARAMS, device=device)
         disc_grads = torch.randn(DISC_PARAMS, device=device) if args.amp else None
         norm_stats = torch.zeros(61, dtype=torch.float64, device=device) if args.amp else None
+        fork = torch.cuda.Event()
 
-    def exchange():
-        for _ in range(20):
-            dist.all_reduce(est_grads, op=dist.ReduceOp.AVG)
-            dist.all_reduce(grads, op=dist.ReduceOp.AVG)
+    N_MSG = 20                                       # 5 epochs x 4 minibatches
+
+    def exchange_slice(k):
+        """Minibatch k's messages, queued on the side stream behind env-step k's fused kernel: they run beside the
+        latency-bound tail of the step (reset ids, terminal rows, reset + fix-up: few CTAs), not across the fused kernel."""
+        if k >= N_MSG:
+            return
+        fork.record()
+        comm_stream.wait_event(fork)
+        with torch.cuda.stream(comm_stream):
+            dist.all_reduce(est_grads, op=dist.ReduceOp.AVG, group=grad_group)
+            dist.all_reduce(grads, op=dist.ReduceOp.AVG, group=grad_group)
             if args.amp:
-                dist.all_reduce(disc_grads, op=dist.ReduceOp.AVG)
-                dist.all_reduce(norm_stats, op=dist.ReduceOp.SUM)
+                dist.all_reduce(disc_grads, op=dist.ReduceOp.AVG, group=grad_group)
+                dist.all_reduce(norm_stats, op=dist.ReduceOp.SUM, group=grad_group)
+
+    def exchange_rest():
+        """Rollouts shorter than 20 env-steps: the remaining messages after the last step."""
+        for k in range(min(args.rollout, N_MSG), N_MSG):
+            exchange_slice(k)
+
+    if comm_stream is not None:
+        wl.exchange_cb = exchange_slice
 
     def step():
-        if comm_stream is not None:
-            comm_stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(comm_stream):
-                exchange()
         wl.rollout(time_fused=True)
         if comm_stream is not None:
+            exchange_rest()
             torch.cuda.current_stream().wait_stream(comm_stream)
 
     for _ in range(max(args.warmup, 3)):
@@ -372,25 +397,31 @@ def run_gpu_arm(args):
                 torch.cuda.synchronize()
                 moments_in_graph = True
                 try:
+                    # world > 1: the collectives are captured too -- the 3-double moments on the rollout's own branch,
+                    # the gradient messages as a forked branch per env-step that joins before the graph ends
                     with torch.cuda.graph(g, stream=s):
-                        wl.rollout(finish=True)          # world > 1: the 3-double moments all-reduce (NCCL) is captured too
+                        wl.rollout(finish=True)
+                        if comm_stream is not None:
+                            exchange_rest()
+                            s.wait_stream(comm_stream)
                 except Exception:
-                    moments_in_graph = False             # NCCL build that cannot be captured: keep that one collective outside
+                    moments_in_graph = False             # NCCL build that cannot be captured: keep the collectives outside
+                    wl.exchange_cb = None
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=s):
                         wl.rollout(finish=(world == 1))
             torch.cuda.current_stream().wait_stream(s)
 
             def graph_step():
-                if comm_stream is not None:
+                if comm_stream is not None and not moments_in_graph:
                     comm_stream.wait_stream(torch.cuda.current_stream())
-                    with torch.cuda.stream(comm_stream):
-                        exchange()
+                    for k in range(N_MSG):
+                        exchange_slice(k)
                 g.replay()
                 if world > 1 and not moments_in_graph:
                     wl.finish()
-                if comm_stream is not None:
-                    torch.cuda.current_stream().wait_stream(comm_stream)
+                    if comm_stream is not None:
+                        torch.cuda.current_stream().wait_stream(comm_stream)
 
             for _ in range(3):
                 graph_step()
@@ -405,6 +436,8 @@ def run_gpu_arm(args):
     value = world * args.envs * args.rollout * args.steps / (ms * 1e-3)
 
     # ---- e2e runs on EVERY rank (it contains collectives: moment all-reduce, barriers)
+    wl.exchange_cb = None
+    wl.env._fused_event_hook = None
     e2e = None if args.no_e2e else measure_e2e(wl, args, world)
     if rank != 0:
         return
@@ -426,7 +459,7 @@ def run_gpu_arm(args):
         "exchange": None if world == 1 else ("off (--no-comm)" if args.no_comm else
                                              "20 x {estimator 59,875 fp32; actor-critic 545,660 fp32 grads + KL scalar (one message)}" +
                                              (" + {discriminator 587,777 fp32 + 61-double normaliser}" if args.amp else "") +
-                                             " all-reduces per rollout on a side stream; 3-double advantage moments inside the rollout"),
+                                             " all-reduces per rollout, message pair k queued on a side stream behind env-step k's fused kernel (own communicator, captured in the graph); 3-double advantage moments inside the rollout on a second communicator"),
         "direct_launch": {"value": world * args.envs * args.rollout * args.steps / (ms_direct * 1e-3), "unit": UNIT,
                           "ms_per_step": ms_direct / args.steps},
     }

@@ -449,6 +449,12 @@ class FusedLeggedRobot:
         r.uniforms = p(self._reset_uniforms)
         return r
 
+    def _uw(self, t):
+        """gymtorch.unwrap_tensor when mixed into the reference env (set `self._unwrap = gymtorch.unwrap_tensor`,
+        INTEGRATION.md §2); identity for replayed / synthetic PhysX state."""
+        f = getattr(self, "_unwrap", None)
+        return f(t) if f is not None else t
+
     def _ids_arg(self, env_ids):
         env_ids = env_ids.to(self.device, torch.long).contiguous()
         return env_ids, torch.tensor([env_ids.numel()], dtype=torch.int32, device=self.device)
@@ -472,14 +478,14 @@ class FusedLeggedRobot:
         self._reset_part(env_ids, L.RESET_DOFS)
         gym = getattr(self, "gym", None)
         if gym is not None and len(env_ids):
-            gym.set_dof_state_tensor_indexed(self.sim, self.dof_state, env_ids.to(torch.int32), len(env_ids))
+            gym.set_dof_state_tensor_indexed(self.sim, self._uw(self.dof_state), self._uw(env_ids.to(torch.int32)), len(env_ids))
 
     def _reset_root_states(self, env_ids):
         """LR:718-820."""
         self._reset_part(env_ids, L.RESET_ROOT)
         gym = getattr(self, "gym", None)
         if gym is not None and len(env_ids):
-            gym.set_actor_root_state_tensor_indexed(self.sim, self.root_states, env_ids.to(torch.int32), len(env_ids))
+            gym.set_actor_root_state_tensor_indexed(self.sim, self._uw(self.root_states), self._uw(env_ids.to(torch.int32)), len(env_ids))
 
     def _resample_commands(self, env_ids):
         """LR:634-656."""
@@ -513,7 +519,7 @@ class FusedLeggedRobot:
         self.root_states[:, 7:9] = (2 * mv) * torch.rand(self.num_envs, 2, device=self.device) - mv
         gym = getattr(self, "gym", None)
         if gym is not None:
-            gym.set_actor_root_state_tensor(self.sim, self.root_states)
+            gym.set_actor_root_state_tensor(self.sim, self._uw(self.root_states))
 
     def _disturbance_robots(self):
         """LR:838-844 (torch RNG; PhysX-facing)."""
@@ -521,7 +527,7 @@ class FusedLeggedRobot:
         self.disturbance[:, 0, :] = (hi - lo) * torch.rand(self.num_envs, 3, device=self.device) + lo
         gym = getattr(self, "gym", None)
         if gym is not None:
-            gym.apply_rigid_body_force_tensors(self.sim, forceTensor=self.disturbance, space="LOCAL_SPACE")
+            gym.apply_rigid_body_force_tensors(self.sim, forceTensor=self._uw(self.disturbance), space=getattr(self, "_local_space", "LOCAL_SPACE"))
 
     def update_command_curriculum(self, env_ids):
         """LR:868-880 (host state: the shared command ranges)."""
@@ -657,8 +663,10 @@ class FusedLeggedRobot:
         gym = getattr(self, "gym", None)
         if gym is not None and n_reset and getattr(self, "_reset_sets_physx", False):
             ids32 = env_ids.to(torch.int32)                   # LR:713-716,817-820: hand the re-drawn rows to PhysX
-            gym.set_dof_state_tensor_indexed(self.sim, self.dof_state, ids32, n_reset)
-            gym.set_actor_root_state_tensor_indexed(self.sim, self.root_states, ids32, n_reset)
+            gym.set_dof_state_tensor_indexed(self.sim, self._uw(self.dof_state), self._uw(ids32), n_reset)
+            gym.set_actor_root_state_tensor_indexed(self.sim, self._uw(self.root_states), self._uw(ids32), n_reset)
+        if n_reset and getattr(self, "_reset_sets_physx", False) and hasattr(self, "refresh_actor_rigid_shape_props"):
+            self.refresh_actor_rigid_shape_props(env_ids)     # LR:343: friction / restitution re-draw (PhysX actor props)
         return env_ids, term_priv[:n_reset], term_amp[:n_reset]
 
     def step(self, actions):
@@ -672,7 +680,7 @@ class FusedLeggedRobot:
         for k in range(self.cfg_hot.decimation):
             self._compute_torques_into(self.delayed_actions[:, k], self.torques)
             if gym is not None:                               # LR:148-152
-                gym.set_dof_actuation_force_tensor(self.sim, self.torques)
+                gym.set_dof_actuation_force_tensor(self.sim, self._uw(self.torques))
                 gym.simulate(self.sim)
                 gym.fetch_results(self.sim, True)
                 gym.refresh_dof_state_tensor(self.sim)
