@@ -342,32 +342,24 @@ def run_gpu_arm(args):
 
     N_MSG = 20                                       # 5 epochs x 4 minibatches
 
-    def exchange_slice(k):
-        """Minibatch k's messages, queued on the side stream behind env-step k's fused kernel: they run beside the
-        latency-bound tail of the step (reset ids, terminal rows, reset + fix-up: few CTAs), not across the fused kernel."""
-        if k >= N_MSG:
-            return
+    def exchange():
+        """All messages of one update, forked onto the side stream at the start of the rollout.  (Queuing pair k behind
+        env-step k's fused kernel instead was measured too: 3.88 vs 3.76 ms per rollout on 8 GPUs, tools/scale_probe.py.)"""
         fork.record()
         comm_stream.wait_event(fork)
         with torch.cuda.stream(comm_stream):
-            dist.all_reduce(est_grads, op=dist.ReduceOp.AVG, group=grad_group)
-            dist.all_reduce(grads, op=dist.ReduceOp.AVG, group=grad_group)
-            if args.amp:
-                dist.all_reduce(disc_grads, op=dist.ReduceOp.AVG, group=grad_group)
-                dist.all_reduce(norm_stats, op=dist.ReduceOp.SUM, group=grad_group)
-
-    def exchange_rest():
-        """Rollouts shorter than 20 env-steps: the remaining messages after the last step."""
-        for k in range(min(args.rollout, N_MSG), N_MSG):
-            exchange_slice(k)
-
-    if comm_stream is not None:
-        wl.exchange_cb = exchange_slice
+            for _ in range(N_MSG):
+                dist.all_reduce(est_grads, op=dist.ReduceOp.AVG, group=grad_group)
+                dist.all_reduce(grads, op=dist.ReduceOp.AVG, group=grad_group)
+                if args.amp:
+                    dist.all_reduce(disc_grads, op=dist.ReduceOp.AVG, group=grad_group)
+                    dist.all_reduce(norm_stats, op=dist.ReduceOp.SUM, group=grad_group)
 
     def step():
+        if comm_stream is not None:
+            exchange()
         wl.rollout(time_fused=True)
         if comm_stream is not None:
-            exchange_rest()
             torch.cuda.current_stream().wait_stream(comm_stream)
 
     for _ in range(max(args.warmup, 3)):
@@ -398,15 +390,15 @@ def run_gpu_arm(args):
                 moments_in_graph = True
                 try:
                     # world > 1: the collectives are captured too -- the 3-double moments on the rollout's own branch,
-                    # the gradient messages as a forked branch per env-step that joins before the graph ends
+                    # the gradient messages as a forked branch that joins before the graph ends
                     with torch.cuda.graph(g, stream=s):
+                        if comm_stream is not None:
+                            exchange()
                         wl.rollout(finish=True)
                         if comm_stream is not None:
-                            exchange_rest()
                             s.wait_stream(comm_stream)
                 except Exception:
                     moments_in_graph = False             # NCCL build that cannot be captured: keep the collectives outside
-                    wl.exchange_cb = None
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=s):
                         wl.rollout(finish=(world == 1))
@@ -414,9 +406,7 @@ def run_gpu_arm(args):
 
             def graph_step():
                 if comm_stream is not None and not moments_in_graph:
-                    comm_stream.wait_stream(torch.cuda.current_stream())
-                    for k in range(N_MSG):
-                        exchange_slice(k)
+                    exchange()
                 g.replay()
                 if world > 1 and not moments_in_graph:
                     wl.finish()
@@ -436,7 +426,6 @@ def run_gpu_arm(args):
     value = world * args.envs * args.rollout * args.steps / (ms * 1e-3)
 
     # ---- e2e runs on EVERY rank (it contains collectives: moment all-reduce, barriers)
-    wl.exchange_cb = None
     wl.env._fused_event_hook = None
     e2e = None if args.no_e2e else measure_e2e(wl, args, world)
     if rank != 0:
@@ -459,7 +448,7 @@ def run_gpu_arm(args):
         "exchange": None if world == 1 else ("off (--no-comm)" if args.no_comm else
                                              "20 x {estimator 59,875 fp32; actor-critic 545,660 fp32 grads + KL scalar (one message)}" +
                                              (" + {discriminator 587,777 fp32 + 61-double normaliser}" if args.amp else "") +
-                                             " all-reduces per rollout, message pair k queued on a side stream behind env-step k's fused kernel (own communicator, captured in the graph); 3-double advantage moments inside the rollout on a second communicator"),
+                                             " all-reduces per rollout on a side stream (own communicator, captured in the graph with the rollout); 3-double advantage moments inside the rollout on a second communicator"),
         "direct_launch": {"value": world * args.envs * args.rollout * args.steps / (ms_direct * 1e-3), "unit": UNIT,
                           "ms_per_step": ms_direct / args.steps},
     }

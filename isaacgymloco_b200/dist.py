@@ -26,9 +26,12 @@ def init_from_env(backend: Optional[str] = None):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
-        # the all-reduces are <= 4.5 MB and overlap the env kernels: keep NCCL to a few CTAs so it
-        # takes fewer SM slots from them (2 GPUs, 65,536 envs each: 4.03 -> 3.93 ms per rollout)
-        os.environ.setdefault("NCCL_MAX_CTAS", "8")
+        # every message of this library is <= 4.5 MB and overlaps the env kernels, so what matters is the latency of a
+        # message while it shares the SMs.  Measured on 8 GPUs (tools/scale_probe.py, profiles/r2_scale_probe_n8.json;
+        # 40 messages per 3.60 ms rollout): NCCL_MAX_CTAS=8 with the tuner's protocol 2.73 ms alone / +0.97 ms overlapped;
+        # 2 CTAs 6.56 / +4.9 ms; the LL protocol on up to 32 CTAs 1.70 ms alone / +0.15 ms overlapped.
+        os.environ.setdefault("NCCL_MAX_CTAS", "32")
+        os.environ.setdefault("NCCL_PROTO", "LL")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
         if backend is None:
