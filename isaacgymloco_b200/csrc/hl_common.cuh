@@ -62,6 +62,9 @@ static inline void hl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size
 // look-back state of a CTA / tile in the ordered reset-id compaction: epoch << 32 | flag << 30 | value
 constexpr unsigned long long HL_LB_AGG = 1ull << 30, HL_LB_PREFIX = 2ull << 30, HL_LB_VALUE = (1ull << 30) - 1ull;
 
+#ifndef HL_TILED_TMA
+#define HL_TILED_TMA 0              // 1: compile the cp.async.bulk staging path into the tiled fused kernel (then HL_FUSED_TMA=1 selects it)
+#endif
 #ifndef HL_PK_WAIT_HINT
 #define HL_PK_WAIT_HINT 0           // ns: mbarrier.try_wait suspend-time hint for long waits; 0 = probe + nanosleep
 #endif
