@@ -3,19 +3,27 @@
 names, attribute names, dtypes and in-place side effects, executed by libhimloco_b200's CUDA
 kernels.
 
-What stays torch (out of scope): everything that draws torch RNG or talks to
-PhysX -- `_resample_commands`, `_reset_dofs`, `_reset_root_states`, pushes, disturbances,
-curricula.  They plug in through the same method names (subclass / mix in the reference class,
-see INTEGRATION.md) and through `physics_step_fn` for replayed or synthetic PhysX state.
+What stays torch / host (out of scope): PhysX itself and every `gym.*` call (issued here in the
+reference's order when `self.gym` exists), pushes and disturbances (torch RNG written into PhysX-owned tensors),
+the host-side command curriculum, friction re-randomisation.  The reset hooks (`_reset_dofs`, `_reset_root_states`,
+`_resample_commands`, `_update_terrain_curriculum`) run in the kernels by default (Philox, or pre-drawn uniforms in
+parity mode); overriding any of them with torch code (subclass / mix in the reference class) makes
+the step fall back to fused -> host sync -> torch reset_idx -> fix-up.  `physics_step_fn` feeds replayed or synthetic
+PhysX state.
 
-Fused step (post_physics_step):
-    [torch] command resample for envs hitting the 500-step mark        LR:612-613
-    hl_post_physics_fused      counters, frame, contacts, heading, 187+63-point scans,
-                               termination, rewards, speculative obs + last_* roll   LR:193-241
-    hl_select_reset_ids        env_ids = reset_buf.nonzero().flatten()              LR:225
-    hl_terminal_rows           termination_privileged_obs, terminal_amp_states      LR:227-228
-    [torch] reset_idx(env_ids)                                                      LR:229
-    hl_post_reset_fixup        re-scan + obs slot 0 + roll for the reset envs       LR:232-241,332-333
+One env-step (post_physics_step_device, no host sync, CUDA-graph capturable):
+    gym.refresh_* x4, common_step_counter += 1                                      LR:187-194
+    [torch] disturbance / push on their interval steps (the push step takes the staged path)   LR:624-632
+    hl_post_physics_fused      command resampling on the interval mark, counters, frame, contacts, heading,
+                               187+63-point scans, termination, rewards, speculative obs + last_* roll
+                               [+ ordered reset ids and terminal rows for shards <= 16,384 envs]   LR:193-241,612-613
+    hl_select_and_terminal     env_ids = reset_buf.nonzero().flatten(); termination_privileged_obs,
+                               terminal_amp_states of those envs                     LR:225-228
+    hl_reset_and_fixup         reset_idx (curriculum, dof / root / command re-draws, gain factors, buffer zeroing,
+                               extras["episode"] means) + re-scan, obs slot 0 and roll of the reset envs
+                                                                                    LR:229-241,288-361
+post_physics_step() adds the one `.item()` its return signature needs, after everything is queued, and hands the
+re-drawn rows to PhysX (`set_*_state_tensor_indexed`).
 """
 import ctypes
 import math
@@ -675,8 +683,8 @@ class FusedLeggedRobot:
         torch.clamp(actions.to(self.device), -clip, clip, out=self.actions)
         self._delay_actions()
         gym = getattr(self, "gym", None)
-        if gym is not None:
-            self.render() if hasattr(self, "render") else None
+        if gym is not None and hasattr(self, "render"):
+            self.render()                                     # LR:131
         for k in range(self.cfg_hot.decimation):
             self._compute_torques_into(self.delayed_actions[:, k], self.torques)
             if gym is not None:                               # LR:148-152
