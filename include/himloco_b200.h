@@ -210,6 +210,9 @@ int hl_terrain_prepare_f32(const int16_t* height_samples, int32_t rows, int32_t 
  * are patched afterwards by hl_post_reset_fixup. */
 int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n_envs, void* stream);
 int64_t hl_fused_workspace_bytes(int64_t n_envs);
+/* Which form the calling thread's last hl_post_physics_fused launch took: 0 = tiled (the default), 1 = persistent
+ * role-pipelined (environment HL_FUSED_IMPL=persist, when the shard qualifies), -1 = none yet.  For tests / tools. */
+int hl_fused_last_impl(void);
 
 /* Any subset of stages, for the individual drop-in methods (check_termination(),
  * compute_reward(), compute_observations(), _get_heights(), ...).  If `env_ids` is non-NULL the

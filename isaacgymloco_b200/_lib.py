@@ -68,6 +68,7 @@ EXPORTS = {
     "hl_terrain_prepare_f32": (c_int32, [_vp, c_int32, c_int32, c_float, _vp, _vp]),
     "hl_post_physics_fused": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), c_int64, _vp]),
     "hl_fused_workspace_bytes": (c_int64, [c_int64]),
+    "hl_fused_last_impl": (c_int32, []),
     "hl_post_physics_stages": (c_int32, [POINTER(HlCfg), POINTER(HlEnvBuffers), c_uint32, _vp, _vp, c_int64, _vp]),
     "hl_select_workspace_bytes": (c_int64, [c_int64]),
     "hl_select_reset_ids": (c_int32, [_vp, c_int64, _vp, _vp, _vp, _vp]),

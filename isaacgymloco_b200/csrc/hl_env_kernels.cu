@@ -1515,6 +1515,9 @@ static int pick_tile(int64_t n) {
   return best;
 }
 
+static thread_local int g_fused_last_impl = -1;
+extern "C" int hl_fused_last_impl(void) { return g_fused_last_impl; }
+
 extern "C" int64_t hl_fused_workspace_bytes(int64_t n) { return (int64_t)(((n + 16 - 1) / 16) + 2) * 8; }  // sized for tiles of >= 16 envs
 
 extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs, int64_t n, void* stream) {
@@ -1596,6 +1599,7 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
     if (prc != HL_E_UNSUPPORTED) {
       if (prc) return prc;
       HL_CHECK_LAUNCH();
+      g_fused_last_impl = 1;
       return HL_OK;
     }
   }
@@ -1621,5 +1625,6 @@ extern "C" int hl_post_physics_fused(const HlCfg* cfg, const HlEnvBuffers* bufs,
   if (rc == HL_E_UNSUPPORTED) rc = fk64::run(cfg, bufs, n, fa, fast, cpu, rmask, st);
   if (rc) return rc;
   HL_CHECK_LAUNCH();
+  g_fused_last_impl = 0;
   return HL_OK;
 }

@@ -33,18 +33,30 @@ def _worker(rank, world, port, fn_name, q):
         dist.destroy_process_group()
 
 
-def _run(fn_name, world=2):
+def _run(fn_name, world=2, attempts=2):
+    """Spawn `world` gloo ranks on a fresh port; a rendezvous that does not complete (the probed port can be taken
+    between the probe and rank 0's bind) is torn down and retried once on another port."""
+    import queue
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, fn_name, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    out = dict(q.get(timeout=120) for _ in range(world))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    return out
+    for attempt in range(attempts):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, fn_name, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        try:
+            out = dict(q.get(timeout=90) for _ in range(world))
+        except queue.Empty:
+            for p in procs:
+                p.terminate()
+                p.join(timeout=10)
+            if attempt + 1 == attempts:
+                raise
+            continue
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        return out
 
 
 def _grad_case(rank, world):
