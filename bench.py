@@ -435,7 +435,9 @@ def run_gpu_arm(args):
     alg_bytes = bytes_tab["post_physics"] * args.envs
     achieved = alg_bytes / (fused_avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "hl_post_physics_fused_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": args.traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": args.traffic,
+                "traffic_source": "ncu dram__bytes_read+write of one launch of this kernel build (profiles/fused_traffic.json; --traffic overrides), not re-measured in this run",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": fused_avg_ms,
                 "bytes_per_env_step": bytes_tab,
                 "whole_step_frac": (bytes_tab["total"] * args.envs * args.rollout * args.steps / (ms * 1e-3) / 1e9) / peak}
