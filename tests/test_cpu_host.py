@@ -204,3 +204,27 @@ def test_integration_mixin_resolves_as_documented():
                  "refresh_actor_rigid_shape_props", "_process_rigid_shape_props", "_get_noise_scale_vec"):
         assert getattr(LeggedRobotB200, name) is getattr(LeggedRobot, name), name
     assert LeggedRobotB200.__mro__[1] is FusedLeggedRobot
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the contract's
+    keys, the real env count of the sample, no GPU launches, and `kind` saying which CPU implementation was timed."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                          capture_output=True, text=True, timeout=600, cwd=root)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "post_physics_gae_env_steps_per_s" and d["unit"] == "env-steps/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["gpu_launches"] == 0
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    if os.path.isdir("/root/reference"):
+        assert cb["kind"] == "reference"          # the reference's own classes under the stub harness
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["sample_envs"] == 4096     # the env count actually timed, stated in the line
