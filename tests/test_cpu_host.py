@@ -228,3 +228,16 @@ def test_reference_arm_prints_the_contract_line():
         assert cb["kind"] == "reference"          # the reference's own classes under the stub harness
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["sample_envs"] == 4096     # the env count actually timed, stated in the line
+
+
+def test_library_holds_sm_100a_code_only():
+    """The in-tree build is native Blackwell code (no PTX-only JIT path, no other arch): every embedded ELF is sm_100a."""
+    import shutil
+    import subprocess
+    from isaacgymloco_b200 import _lib as L
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "-lelf", L.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+    elfs = [l for l in out.splitlines() if "ELF file" in l]
+    assert elfs and all("sm_100a" in l for l in elfs), out
